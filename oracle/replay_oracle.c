@@ -1,0 +1,198 @@
+/* oracle/replay_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of the tape-replay algorithms of Adept 2.1.3 (the
+ * reference under /root/reference), written from the algorithm, not from the
+ * code.  It exists so that the CUDA path can be checked on machines where the
+ * reference sources are absent (the GPU box).  It is pinned against the real
+ * reference (oracle/_ref/libadept_ref.so, built by oracle/Makefile from the
+ * unmodified sources) and against the committed golden vectors in
+ * tests/golden/ by tests/test_oracle.py.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load this library.
+ *
+ * Compile with -ffp-contract=off: parity is "multiply, round, add, round".
+ *
+ * Tape layout (include/adept/Statement.h:24-30, StackStorageOrig.h:155-163):
+ *   stmt[2*s] = LHS slot, stmt[2*s+1] = end_plus_one; stmt[0..1] = {-1, 0} is
+ *   the sentinel pushed by new_recording (Stack.h:528-543); statement s owns
+ *   operations [stmt[2*(s-1)+1], stmt[2*s+1]).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define LHS(s) stmt[2*(s)]
+#define END(s) stmt[2*(s)+1]
+
+/* adept/Stack.cpp:170-190 -- forward sweep of ONE gradient vector, in place:
+   a starts at +0.0, operands are accumulated in tape order, no zero skip. */
+void oracle_tangent_linear(const int32_t* stmt, int64_t n_stmt,
+                           const double* mult, const int32_t* idx, double* g) {
+  for (int64_t s = 1; s < n_stmt; ++s) {
+    double a = 0.0;
+    for (int64_t op = END(s-1); op < END(s); ++op) a += mult[op]*g[idx[op]];
+    g[LHS(s)] = a;
+  }
+}
+
+/* adept/Stack.cpp:139-164 -- reverse sweep of ONE gradient vector, in place:
+   a = g[lhs]; g[lhs] = 0; if a is non-zero scatter m*a to the operands in tape order. */
+void oracle_adjoint(const int32_t* stmt, int64_t n_stmt,
+                    const double* mult, const int32_t* idx, double* g) {
+  for (int64_t s = n_stmt-1; s > 0; --s) {
+    double a = g[LHS(s)];
+    g[LHS(s)] = 0.0;
+    if (a != 0.0)
+      for (int64_t op = END(s-1); op < END(s); ++op) g[idx[op]] += mult[op]*a;
+  }
+}
+
+/* Offset defaulting of the raw-pointer entry points (adept/jacobian.cpp:215-220, :473-478):
+   a non-positive offset means "the size of the OTHER dimension". */
+static void default_offsets(int64_t n_indep, int64_t n_dep, int64_t* dep_offset, int64_t* indep_offset) {
+  if (*dep_offset <= 0)   *dep_offset = n_indep;
+  if (*indep_offset <= 0) *indep_offset = n_dep;
+}
+
+/* adept/jacobian.cpp:127-315 -- forward Jacobian in blocks of P independents.
+   Per block: zero G*P workspace, seed g[indep[j]*P + lane] = 1, sweep all
+   lanes, copy out out[i*dep_offset + j*indep_offset] = g[dep[i]*P + lane].
+   Returns 10 if either list is empty (dependents_or_independents_not_identified, :208-210). */
+int oracle_jacobian_forward(const int32_t* stmt, int64_t n_stmt, const double* mult, const int32_t* idx,
+                            int64_t max_gradient, const int32_t* indep, int64_t n_indep,
+                            const int32_t* dep, int64_t n_dep, double* out,
+                            int64_t dep_offset, int64_t indep_offset, int P, int n_threads) {
+  if (n_indep == 0 || n_dep == 0) return 10;
+  default_offsets(n_indep, n_dep, &dep_offset, &indep_offset);
+  int64_t n_block = (n_indep + P - 1)/P;
+  int failed = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+#endif
+  {
+    double* g = (double*)malloc(sizeof(double)*(size_t)max_gradient*P);
+    double* a = (double*)malloc(sizeof(double)*P);
+    if (!g || !a) failed = 1;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int64_t b = 0; b < n_block; ++b) {
+      if (failed) continue;
+      int64_t j0 = b*P;
+      int w = (int)((n_indep - j0 < P) ? (n_indep - j0) : P);
+      memset(g, 0, sizeof(double)*(size_t)max_gradient*P);
+      for (int l = 0; l < w; ++l) g[(int64_t)indep[j0+l]*P + l] = 1.0;
+      for (int64_t s = 1; s < n_stmt; ++s) {
+        for (int l = 0; l < w; ++l) a[l] = 0.0;
+        for (int64_t op = END(s-1); op < END(s); ++op) {
+          const double m = mult[op];
+          const double* src = g + (int64_t)idx[op]*P;
+          for (int l = 0; l < w; ++l) a[l] += m*src[l];
+        }
+        double* dst = g + (int64_t)LHS(s)*P;
+        for (int l = 0; l < w; ++l) dst[l] = a[l];
+      }
+      for (int64_t i = 0; i < n_dep; ++i)
+        for (int l = 0; l < w; ++l)
+          out[i*dep_offset + (j0+l)*indep_offset] = g[(int64_t)dep[i]*P + l];
+    }
+    free(g); free(a);
+  }
+  return failed ? 1 : 0;
+}
+
+/* adept/jacobian.cpp:331-647 -- reverse Jacobian in blocks of P dependents.
+   Per block: zero, seed g[dep[i]][lane] = 1, backward sweep; a statement is
+   skipped only when ALL lanes of the block hold zero (the per-lane sparse branch
+   behind "#if MULTIPASS_SIZE > MULTIPASS_SIZE_ZERO_CHECK" is never compiled:
+   neither name is a macro, :387), otherwise every lane is updated; copy out
+   out[j*indep_offset + i*dep_offset] = g[indep[j]][lane]. */
+int oracle_jacobian_reverse(const int32_t* stmt, int64_t n_stmt, const double* mult, const int32_t* idx,
+                            int64_t max_gradient, const int32_t* indep, int64_t n_indep,
+                            const int32_t* dep, int64_t n_dep, double* out,
+                            int64_t dep_offset, int64_t indep_offset, int P, int n_threads) {
+  if (n_indep == 0 || n_dep == 0) return 10;
+  default_offsets(n_indep, n_dep, &dep_offset, &indep_offset);
+  int64_t n_block = (n_dep + P - 1)/P;
+  int failed = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+#endif
+  {
+    double* g = (double*)malloc(sizeof(double)*(size_t)max_gradient*P);
+    double* a = (double*)malloc(sizeof(double)*P);
+    if (!g || !a) failed = 1;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int64_t b = 0; b < n_block; ++b) {
+      if (failed) continue;
+      int64_t i0 = b*P;
+      int w = (int)((n_dep - i0 < P) ? (n_dep - i0) : P);
+      memset(g, 0, sizeof(double)*(size_t)max_gradient*P);
+      for (int l = 0; l < w; ++l) g[(int64_t)dep[i0+l]*P + l] = 1.0;
+      for (int64_t s = n_stmt-1; s > 0; --s) {
+        double* lhs = g + (int64_t)LHS(s)*P;
+        int any = 0;
+        for (int l = 0; l < w; ++l) { a[l] = lhs[l]; lhs[l] = 0.0; if (a[l] != 0.0) any = 1; }
+        if (!any) continue;
+        for (int64_t op = END(s-1); op < END(s); ++op) {
+          const double m = mult[op];
+          double* dst = g + (int64_t)idx[op]*P;
+          for (int l = 0; l < w; ++l) dst[l] += m*a[l];
+        }
+      }
+      for (int64_t j = 0; j < n_indep; ++j)
+        for (int l = 0; l < w; ++l)
+          out[j*indep_offset + (i0+l)*dep_offset] = g[(int64_t)indep[j]*P + l];
+    }
+    free(g); free(a);
+  }
+  return failed ? 1 : 0;
+}
+
+/* Sequential reference for the dependency analysis the CUDA engine does on the
+   device (no counterpart in the reference: it replays strictly in tape order).
+   level[s] (1-based, level[0] = 0 for the sentinel) is the earliest step at
+   which statement s may run if statements are only reordered in ways that
+   cannot change any bit of the result:
+     mode 0 (gather sweeps, forward): RAW, WAR and WAW on slots are kept;
+                                      concurrent readers of a slot are allowed.
+     mode 1 (scatter sweeps, reverse): every pair of statements touching a common
+                                      slot keeps its tape order (so that the
+                                      accumulation order into each slot is the
+                                      reference's: statement descending, operand
+                                      ascending).
+   Returns the number of levels. */
+int64_t oracle_levels(const int32_t* stmt, int64_t n_stmt, const int32_t* idx,
+                      int64_t max_gradient, int mode, int32_t* level) {
+  int32_t* wl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* level of last writer  */
+  int32_t* rl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* max level of readers since */
+  int32_t depth = 0;
+  level[0] = 0;
+  for (int64_t s = 1; s < n_stmt; ++s) {
+    int32_t lv = 0;
+    int32_t L = LHS(s);
+    for (int64_t op = END(s-1); op < END(s); ++op) {
+      int32_t x = idx[op];
+      if (wl[x] > lv) lv = wl[x];
+      if (mode == 1 && rl[x] > lv) lv = rl[x];
+    }
+    if (wl[L] > lv) lv = wl[L];
+    if (rl[L] > lv) lv = rl[L];
+    lv += 1;
+    level[s] = lv;
+    for (int64_t op = END(s-1); op < END(s); ++op) {
+      int32_t x = idx[op];
+      if (lv > rl[x]) rl[x] = lv;
+    }
+    wl[L] = lv; rl[L] = (mode == 1) ? lv : 0;
+    /* a statement that reads its own LHS: in mode 0 the read belongs to the old
+       version, which this write retires, so rl is reset above. */
+    if (lv > depth) depth = lv;
+  }
+  free(wl); free(rl);
+  return depth;
+}
