@@ -1,0 +1,1270 @@
+// engine.cu -- libadept_cuda: context, tape upload, schedule construction, replay drivers
+// and the C-ABI of include/adept_cuda.h.  Device code lives in *_kernels.cuh.
+//
+// Drop-in boundary: the entry points below stand in for the bodies of
+//   Stack::jacobian_forward / jacobian_reverse   (reference adept/jacobian.cpp:127-647)
+//   Stack::compute_tangent_linear / compute_adjoint (reference adept/Stack.cpp:139-190)
+// Host code here is plumbing (memory, streams, NCCL); there is no CPU replay path.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/adept_cuda.h"
+#include "common.cuh"
+#include "replay_kernels.cuh"
+#include "sweep1_kernels.cuh"
+#include "tape_kernels.cuh"
+
+using namespace adept_b200;
+
+namespace {
+
+constexpr int64_t kChunkRecs = 512;          // target records per level chunk
+constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
+constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
+constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
+constexpr size_t kStageBytes = size_t(32) << 20;
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct LongStmt {
+  int64_t j;      // position in the schedule
+  int32_t level;
+  int64_t b, e;   // record range in the level-major forward stream
+};
+
+struct Shard {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  ncclComm_t comm = nullptr;
+  int sm_count = 148;
+  // pinned staging ring for pageable uploads
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // the tape as recorded
+  Buf stmt, mult, idx;
+  int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
+  bool have_tape = false;
+  // tape-order streams
+  Buf fwd_t, rev_t, one_chunk;
+  int64_t R = 0;
+  // level schedule
+  bool have_levels = false;
+  Buf level, fwd_l, fwd_chunk, foff, sched_lhs;   // level-major forward stream and its tables
+  Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups
+  int32_t n_levels = 0;                            // number of steps
+  int64_t n_chunks = 0, n_tchunks = 0, n_groups = 0, R_t = 0, max_step_width = 0;
+  std::vector<int64_t> level_chunk;   // [n_levels+2] first forward chunk of each step
+  std::vector<int64_t> level_first;   // [n_levels+2] first schedule position of each step
+  std::vector<int64_t> step_group;    // [n_levels+2] first target group of each step
+  std::vector<int64_t> step_tchunk;   // [n_levels+2] first target chunk of each step
+  std::vector<LongStmt> long_stmts;
+  // workspace
+  Buf g, abuf, seed_slots, out_slots, out, g1, a1, scratch;
+  // optional per-launch timing of the dominant replay kernel (option "time_kernels")
+  std::vector<cudaEvent_t> kev;
+  size_t kev_used = 0;
+  // per-shard bookkeeping (shards may be driven by worker threads)
+  std::string err;
+  double launches = 0;
+  std::map<std::string, double> stat;
+};
+
+}  // namespace
+
+struct adept_cuda_ctx {
+  std::vector<Shard> sh;
+  int world = 1;       // total ranks (devices over all processes)
+  int rank0 = 0;       // global rank of sh[0]
+  bool multi_process = false;
+  uint64_t epoch = 0;
+  // options
+  int opt_schedule = 0, opt_ref_block = 2, opt_warps = 8;
+  int64_t opt_pass_dirs = 0, opt_workspace_bytes = 0, opt_window = 0;
+  int opt_time_kernels = 0;
+  // stats
+  std::map<std::string, double> stat;
+  std::string err;
+  double total_launches() const {
+    double n = 0;
+    for (const Shard& s : sh) n += s.launches;
+    return n;
+  }
+};
+
+namespace {
+
+// Errors are written to whatever std::string* named `errp` is in scope: the context's in the
+// C-ABI functions, the shard's own inside per-shard work (which may run on worker threads).
+int fail(std::string* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) *e = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(errp, ADEPT_CUDA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                             \
+  } while (0)
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      return fail(errp, ADEPT_CUDA_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), \
+                  __FILE__, __LINE__);                                                             \
+  } while (0)
+#define RET(call)                \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_) return rc_;         \
+  } while (0)
+
+int ensure(std::string* errp, Buf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.bytes >= bytes) return 0;
+  if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(errp, ADEPT_CUDA_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  b.bytes = bytes;
+  return 0;
+}
+void release(Buf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+inline int grid_for(int64_t n, int block, int sm_count) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = int64_t(sm_count) * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return int(g);
+}
+
+int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
+  int b = 1;
+  while ((int64_t(1) << b) < n && b < 32) ++b;
+  return b;
+}
+
+// H2D of one array: pinned sources are DMA'd directly; pageable ones go through a two-slot
+// pinned ring so the host memcpy of piece k+1 overlaps the DMA of piece k.
+int upload(Shard& s, void* dst, const void* src, size_t bytes) {
+  std::string* errp = &s.err;
+  if (bytes == 0) return 0;
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+  else cudaGetLastError();
+  if (pinned) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
+    return 0;
+  }
+  for (int k = 0; k < 2; ++k)
+    if (!s.stage[k]) {
+      CK(cudaMallocHost(&s.stage[k], kStageBytes));
+      CK(cudaEventCreateWithFlags(&s.stage_ev[k], cudaEventDisableTiming));
+    }
+  size_t off = 0;
+  int k = 0;
+  while (off < bytes) {
+    const size_t n = std::min(kStageBytes, bytes - off);
+    CK(cudaEventSynchronize(s.stage_ev[k]));
+    std::memcpy(s.stage[k], static_cast<const char*>(src) + off, n);
+    CK(cudaMemcpyAsync(static_cast<char*>(dst) + off, s.stage[k], n, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaEventRecord(s.stage_ev[k], s.stream));
+    off += n;
+    k ^= 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Schedule construction on one shard (tape already on the device).
+// ---------------------------------------------------------------------------------------
+struct BufSet {  // temporaries freed on every exit path
+  std::vector<Buf*> all;
+  Buf& add(Buf& b) { all.push_back(&b); return b; }
+  ~BufSet() { for (Buf* b : all) release(*b); }
+};
+
+int sort_pairs(std::string* errp, Shard& s, Buf& k0, Buf& k1, Buf& v0, Buf& v1, Buf& tmp, int64_t n, int nbits) {
+  cub::DoubleBuffer<uint32_t> dk(k0.as<uint32_t>(), k1.as<uint32_t>());
+  cub::DoubleBuffer<uint32_t> dv(v0.as<uint32_t>(), v1.as<uint32_t>());
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, n, 0, nbits, s.stream));
+  RET(ensure(errp, tmp, tb));
+  CK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, n, 0, nbits, s.stream));
+  if (dk.Current() != k0.as<uint32_t>()) std::swap(k0, k1);
+  if (dv.Current() != v0.as<uint32_t>()) std::swap(v0, v1);
+  return 0;  // sorted keys in k0, values in v0
+}
+
+template <class T>
+int exclusive_sum(std::string* errp, Shard& s, Buf& tmp, const T* in, T* out, int64_t n) {
+  size_t tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s.stream));
+  RET(ensure(errp, tmp, tb));
+  CK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, s.stream));
+  return 0;
+}
+template <class T>
+int inclusive_sum(std::string* errp, Shard& s, Buf& tmp, const T* in, T* out, int64_t n) {
+  size_t tb = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, s.stream));
+  RET(ensure(errp, tmp, tb));
+  CK(cub::DeviceScan::InclusiveSum(tmp.p, tb, in, out, n, s.stream));
+  return 0;
+}
+
+int build_schedule(const adept_cuda_ctx* c, Shard& s) {
+  std::string* errp = &s.err;
+  CK(cudaSetDevice(s.dev));
+  const int64_t S = s.n_stmt - 1, O = s.n_ops, R = O + S;
+  s.R = R;
+  s.have_levels = false;
+  s.n_levels = 0;
+  s.n_chunks = 0;
+  s.n_tchunks = 0;
+  s.n_groups = 0;
+  s.max_step_width = 0;
+  s.long_stmts.clear();
+  if (s.n_stmt < 1) return fail(errp, ADEPT_CUDA_ERR_ARG, "tape has no sentinel statement");
+  if (R >= (int64_t(1) << 31) - 1)
+    return fail(errp, ADEPT_CUDA_ERR_LIMIT, "tape too long: n_ops + n_statements = %lld >= 2^31", (long long)R);
+  const int T = 256;
+  // 1. validate (a bad slot would otherwise be a wild device access)
+  RET(ensure(errp, s.scratch, 64));
+  CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
+  validate_kernel<<<grid_for(std::max(O, s.n_stmt), T, s.sm_count), T, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), O, s.max_gradient, s.scratch.as<int>());
+  s.launches += 1;
+  int flags = 0;
+  CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  if (flags)
+    return fail(errp, ADEPT_CUDA_ERR_RANGE,
+                "malformed tape: a slot index is outside [0,max_gradient) or statement ends are not monotone");
+  // 2. tape-order streams
+  const int64_t one_chunk_host[2] = {0, R};
+  RET(ensure(errp, s.one_chunk, sizeof one_chunk_host));
+  CK(cudaMemcpyAsync(s.one_chunk.p, one_chunk_host, sizeof one_chunk_host, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaStreamSynchronize(s.stream));  // one_chunk_host is a stack variable
+  if (S == 0) return 0;
+  RET(ensure(errp, s.fwd_t, size_t(R) * sizeof(Rec)));
+  RET(ensure(errp, s.rev_t, size_t(R) * sizeof(Rec)));
+  build_streams_kernel<<<grid_for(std::max(O, S), T, s.sm_count), T, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), O, s.fwd_t.as<Rec>(),
+      s.rev_t.as<Rec>(), nullptr);
+  s.launches += 1;
+  CK(cudaGetLastError());
+  const bool want_levels = (c->opt_schedule != 1) && (S >= kMinLevelStatements || c->opt_schedule == 2);
+  if (!want_levels) return 0;
+
+  BufSet tmps;
+  Buf cap, tab_off, tables, wdepth, wbase, k0, k1, v0, v1, tmp, nrec, lfirst, flag, cid, lchunk, pos_in_sched, incl,
+      gstep, cflag, cincl, sgroup, stchunk, lo, lc;
+  for (Buf* b : {&cap, &tab_off, &tables, &wdepth, &wbase, &k0, &k1, &v0, &v1, &tmp, &nrec, &lfirst, &flag, &cid,
+                 &lchunk, &pos_in_sched, &incl, &gstep, &cflag, &cincl, &sgroup, &stchunk, &lo, &lc})
+    tmps.add(*b);
+
+  // 3. dependency analysis: one warp per window of statements (tape_kernels.cuh)
+  const int64_t W = c->opt_window > 0 ? c->opt_window : kDefaultWindow;
+  const int64_t n_windows = (S + W - 1) / W;
+  RET(ensure(errp, cap, size_t(n_windows + 1) * 8));
+  RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
+  window_caps_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, W,
+                                                                                n_windows, cap.as<int64_t>());
+  s.launches += 1;
+  RET(exclusive_sum(errp, s, tmp, cap.as<int64_t>(), tab_off.as<int64_t>(), n_windows + 1));
+  int64_t total_entries = 0;
+  CK(cudaMemcpyAsync(&total_entries, tab_off.as<int64_t>() + n_windows, 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  RET(ensure(errp, tables, size_t(total_entries) * sizeof(SlotEntry)));
+  CK(cudaMemsetAsync(tables.p, 0xFF, size_t(total_entries) * sizeof(SlotEntry), s.stream));
+  RET(ensure(errp, s.level, size_t(s.n_stmt) * 4));
+  RET(ensure(errp, wdepth, size_t(n_windows + 1) * 4));
+  RET(ensure(errp, wbase, size_t(n_windows + 1) * 4));
+  CK(cudaMemsetAsync(wdepth.p, 0, size_t(n_windows + 1) * 4, s.stream));
+  window_levels_kernel<<<unsigned((n_windows * 32 + 127) / 128), 128, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), W, n_windows, tables.as<SlotEntry>(), tab_off.as<int64_t>(),
+      s.level.as<int32_t>(), wdepth.as<int32_t>());
+  s.launches += 1;
+  RET(exclusive_sum(errp, s, tmp, wdepth.as<int32_t>(), wbase.as<int32_t>(), n_windows + 1));
+  int32_t n_levels = 0;
+  CK(cudaMemcpyAsync(&n_levels, wbase.as<int32_t>() + n_windows, 4, cudaMemcpyDeviceToHost, s.stream));
+  global_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), s.n_stmt, W,
+                                                                      wbase.as<int32_t>());
+  s.launches += 1;
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaGetLastError());
+  release(tables);
+  s.n_levels = n_levels;
+  if (n_levels < 1) return fail(errp, ADEPT_CUDA_ERR_CUDA, "dependency analysis produced no steps");
+
+  // 4. statements sorted by step (stable), record offsets, chunk table, level-major forward stream
+  const int64_t nmax = std::max(S, O);
+  RET(ensure(errp, k0, size_t(nmax) * 4));
+  RET(ensure(errp, k1, size_t(nmax) * 4));
+  RET(ensure(errp, v0, size_t(nmax) * 4));
+  RET(ensure(errp, v1, size_t(nmax) * 4));
+  level_keys_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), S, k0.as<uint32_t>(),
+                                                                    v0.as<uint32_t>());
+  s.launches += 1;
+  RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, S, bits_for(int64_t(n_levels) + 1)));
+  // k0 = step of scheduled statement j, v0 = its statement id
+  RET(ensure(errp, nrec, size_t(S + 1) * 8));
+  RET(ensure(errp, s.foff, size_t(S + 1) * 8));
+  RET(ensure(errp, lfirst, size_t(n_levels + 2) * 8));
+  CK(cudaMemsetAsync(nrec.p, 0, size_t(S + 1) * 8, s.stream));
+  sched_sizes_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(
+      s.stmt.as<int2>(), v0.as<uint32_t>(), k0.as<uint32_t>(), S, n_levels, nrec.as<int64_t>(),
+      lfirst.as<int64_t>());
+  s.launches += 1;
+  RET(exclusive_sum(errp, s, tmp, nrec.as<int64_t>(), s.foff.as<int64_t>(), S + 1));
+  RET(ensure(errp, flag, size_t(nmax + 1) * 4));
+  RET(ensure(errp, cid, size_t(S + 1) * 4));
+  CK(cudaMemsetAsync(flag.p, 0, size_t(S + 1) * 4, s.stream));
+  chunk_flags_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), k0.as<uint32_t>(), S,
+                                                                     kChunkRecs, flag.as<int32_t>());
+  s.launches += 1;
+  RET(exclusive_sum(errp, s, tmp, flag.as<int32_t>(), cid.as<int32_t>(), S + 1));
+  int32_t n_chunks32 = 0;
+  CK(cudaMemcpyAsync(&n_chunks32, cid.as<int32_t>() + S, 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  const int64_t n_chunks = n_chunks32;
+  s.n_chunks = n_chunks;
+  RET(ensure(errp, s.fwd_chunk, size_t(n_chunks + 1) * 8));
+  RET(ensure(errp, lchunk, size_t(n_levels + 2) * 8));
+  chunk_tables_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(
+      s.foff.as<int64_t>(), flag.as<int32_t>(), cid.as<int32_t>(), S, R, n_chunks, lfirst.as<int64_t>(), n_levels,
+      s.fwd_chunk.as<int64_t>(), nullptr, lchunk.as<int64_t>());
+  s.launches += 1;
+  RET(ensure(errp, s.fwd_l, size_t(R) * sizeof(Rec)));
+  emit_level_streams_kernel<<<grid_for(R, T, s.sm_count), T, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.mult.as<double>(), s.idx.as<int32_t>(), v0.as<uint32_t>(), s.foff.as<int64_t>(), S, R,
+      s.fwd_l.as<Rec>(), nullptr);
+  s.launches += 1;
+  RET(ensure(errp, s.sched_lhs, size_t(S) * 4));
+  RET(ensure(errp, pos_in_sched, size_t(s.n_stmt) * 4));
+  sched_lookup_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), v0.as<uint32_t>(), S,
+                                                                      s.sched_lhs.as<int32_t>(),
+                                                                      pos_in_sched.as<int32_t>());
+  s.launches += 1;
+  s.level_chunk.assign(size_t(n_levels) + 2, 0);
+  s.level_first.assign(size_t(n_levels) + 2, 0);
+  CK(cudaMemcpyAsync(s.level_chunk.data(), lchunk.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(s.level_first.data(), lfirst.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  for (int32_t l = 1; l <= n_levels; ++l)
+    s.max_step_width = std::max(s.max_step_width, s.level_first[l + 1] - s.level_first[l]);
+
+  // 5. reverse target stream: operations sorted by (step, slot, reference reverse order)
+  s.step_group.assign(size_t(n_levels) + 2, 0);
+  s.step_tchunk.assign(size_t(n_levels) + 2, 0);
+  if (O > 0) {
+    target_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt,
+                                                                       s.idx.as<int32_t>(), O, k0.as<uint32_t>(),
+                                                                       v0.as<uint32_t>());
+    s.launches += 1;
+    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(s.max_gradient)));
+    target_step_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
+        s.stmt.as<int2>(), s.n_stmt, v0.as<uint32_t>(), O, s.level.as<int32_t>(), k0.as<uint32_t>());
+    s.launches += 1;
+    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(int64_t(n_levels) + 1)));
+    target_flags_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), v0.as<uint32_t>(),
+                                                                        s.idx.as<int32_t>(), O, flag.as<int32_t>());
+    s.launches += 1;
+    RET(ensure(errp, incl, size_t(O) * 4));
+    RET(inclusive_sum(errp, s, tmp, flag.as<int32_t>(), incl.as<int32_t>(), O));
+    int32_t n_groups32 = 0;
+    CK(cudaMemcpyAsync(&n_groups32, incl.as<int32_t>() + (O - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    const int64_t n_groups = n_groups32;
+    const int64_t R_t = O + n_groups;
+    s.n_groups = n_groups;
+    s.R_t = R_t;
+    RET(ensure(errp, s.tgt, size_t(R_t) * sizeof(Rec)));
+    RET(ensure(errp, s.goff, size_t(n_groups + 1) * 8));
+    RET(ensure(errp, gstep, size_t(n_groups + 1) * 4));
+    target_emit_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
+        s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), k0.as<uint32_t>(), v0.as<uint32_t>(),
+        flag.as<int32_t>(), incl.as<int32_t>(), O, pos_in_sched.as<int32_t>(), lfirst.as<int64_t>(),
+        s.tgt.as<Rec>(), s.goff.as<int64_t>(), gstep.as<int32_t>());
+    s.launches += 1;
+    CK(cudaMemcpyAsync(s.goff.as<int64_t>() + n_groups, &s.R_t, 8, cudaMemcpyHostToDevice, s.stream));
+    RET(ensure(errp, cflag, size_t(n_groups + 1) * 4));
+    RET(ensure(errp, cincl, size_t(n_groups + 1) * 4));
+    RET(ensure(errp, sgroup, size_t(n_levels + 2) * 8));
+    RET(ensure(errp, stchunk, size_t(n_levels + 2) * 8));
+    CK(cudaMemsetAsync(sgroup.p, 0xFF, size_t(n_levels + 2) * 8, s.stream));
+    target_chunk_flags_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(
+        s.goff.as<int64_t>(), gstep.as<int32_t>(), n_groups, kChunkRecs, cflag.as<int32_t>(), sgroup.as<int64_t>());
+    s.launches += 1;
+    RET(inclusive_sum(errp, s, tmp, cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups));
+    int32_t n_tchunks32 = 0;
+    CK(cudaMemcpyAsync(&n_tchunks32, cincl.as<int32_t>() + (n_groups - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    s.n_tchunks = n_tchunks32;
+    RET(ensure(errp, s.tchunk, size_t(s.n_tchunks + 1) * 8));
+    target_chunk_table_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(
+        s.goff.as<int64_t>(), cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups, s.n_tchunks, R_t,
+        s.tchunk.as<int64_t>());
+    target_step_tables_kernel<<<1, 1, 0, s.stream>>>(sgroup.as<int64_t>(), n_levels, n_groups, cincl.as<int32_t>(),
+                                                     s.n_tchunks, stchunk.as<int64_t>());
+    s.launches += 2;
+    CK(cudaMemcpyAsync(s.step_group.data(), sgroup.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.step_tchunk.data(), stchunk.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+  }
+
+  // 6. long statements (rare): listed for the single-direction forward sweep
+  {
+    const int max_long = 4096;
+    RET(ensure(errp, lo, size_t(max_long) * 8));
+    RET(ensure(errp, lc, 16));
+    CK(cudaMemsetAsync(lc.p, 0, 16, s.stream));
+    find_long_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), S, kLongThreshold,
+                                                                     lo.as<int64_t>(), lc.as<int>(), max_long);
+    s.launches += 1;
+    int nl = 0;
+    std::vector<int64_t> js(max_long);
+    CK(cudaMemcpyAsync(&nl, lc.p, 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(js.data(), lo.p, size_t(max_long) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (nl > max_long)
+      return fail(errp, ADEPT_CUDA_ERR_LIMIT, "more than %d statements longer than %lld operands", max_long,
+                  (long long)kLongThreshold);
+    js.resize(nl);
+    std::sort(js.begin(), js.end());
+    int64_t ends[2];
+    for (int64_t j : js) {
+      LongStmt L;
+      L.j = j;
+      // step of schedule position j: last l with level_first[l] <= j
+      L.level = int32_t(std::upper_bound(s.level_first.begin() + 1, s.level_first.begin() + n_levels + 1, j) -
+                        s.level_first.begin()) - 1;
+      CK(cudaMemcpy(ends, s.foff.as<int64_t>() + j, 16, cudaMemcpyDeviceToHost));
+      L.b = ends[0];
+      L.e = ends[1];
+      s.long_stmts.push_back(L);
+    }
+  }
+  CK(cudaGetLastError());
+  s.have_levels = true;
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Replay drivers
+// ---------------------------------------------------------------------------------------
+struct SweepPlan {
+  bool use_levels;
+  int warps;
+};
+
+SweepPlan plan_sweep(const adept_cuda_ctx* c, const Shard& s, int64_t n_dirs) {
+  SweepPlan p;
+  p.use_levels = false;
+  if (c->opt_schedule == 1 || !s.have_levels) p.use_levels = false;
+  else if (c->opt_schedule == 2) p.use_levels = true;
+  else {
+    // the level schedule pays when a level offers more parallel work than one launch costs
+    const double stmts_per_level = double(s.n_stmt - 1) / std::max(1, s.n_levels);
+    p.use_levels = stmts_per_level >= 16.0;
+  }
+  p.warps = c->opt_warps;
+  if (p.warps < 1) p.warps = 1;
+  if (p.warps > 8) p.warps = 8;
+  const int64_t ncb = (n_dirs + 31) / 32;
+  if (!p.use_levels) {
+    // tape-ordered: one chunk, so spread the column blocks over as many CTAs as possible
+    const int64_t per = std::max<int64_t>(1, ncb / (2 * s.sm_count));
+    p.warps = int(std::min<int64_t>(p.warps, per));
+  } else {
+    if (ncb < p.warps) p.warps = int(ncb);
+  }
+  if (p.warps < 1) p.warps = 1;
+  return p;
+}
+
+// next event of the per-launch timing pool, recorded on the shard's stream
+int mark(Shard& s) {
+  std::string* errp = &s.err;
+  if (s.kev_used == s.kev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    s.kev.push_back(e);
+  }
+  CK(cudaEventRecord(s.kev[s.kev_used++], s.stream));
+  return 0;
+}
+
+// One sweep over the resident pass (g already zeroed and seeded).  mode: 0 forward, 1 reverse.
+int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t K, int64_t n_dirs,
+                 const SweepPlan& plan) {
+  std::string* errp = &s.err;
+  if (s.R == 0) return 0;
+  ReplayArgs A;
+  A.g = g;
+  A.K = K;
+  A.n_colblocks = int((n_dirs + 31) / 32);
+  A.n_dirs = n_dirs;
+  A.ref_block = c->opt_ref_block;
+  const int threads = plan.warps * 32;
+  const unsigned gy = unsigned((A.n_colblocks + plan.warps - 1) / plan.warps);
+  if (!plan.use_levels) {
+    A.recs = (mode == 0 ? s.fwd_t : s.rev_t).as<Rec>();
+    A.chunk_begin = s.one_chunk.as<int64_t>();
+    A.first_chunk = 0;
+    if (c->opt_time_kernels) RET(mark(s));
+    if (mode == 0) replay_forward_kernel<true><<<dim3(1, gy), threads, 0, s.stream>>>(A);
+    else replay_reverse_kernel<<<dim3(1, gy), threads, 0, s.stream>>>(A);
+    if (c->opt_time_kernels) RET(mark(s));
+    s.launches += 1;
+  } else if (mode == 0) {
+    A.recs = s.fwd_l.as<Rec>();
+    A.chunk_begin = s.fwd_chunk.as<int64_t>();
+    for (int32_t l = 1; l <= s.n_levels; ++l) {
+      const int64_t c0 = s.level_chunk[l], c1 = s.level_chunk[l + 1];
+      if (c1 <= c0) continue;
+      A.first_chunk = c0;
+      if (c->opt_time_kernels) RET(mark(s));
+      replay_forward_kernel<false><<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(A);
+      if (c->opt_time_kernels) RET(mark(s));
+      s.launches += 1;
+    }
+  } else {
+    // reverse: steps downwards; per step snapshot a_s and zero the LHS slots, then gather per target
+    TargetArgs B;
+    B.recs = s.tgt.as<Rec>();
+    B.chunk_begin = s.tchunk.as<int64_t>();
+    B.g = g;
+    B.abuf = s.abuf.as<double>();
+    B.K = K;
+    B.n_colblocks = A.n_colblocks;
+    B.n_dirs = n_dirs;
+    B.ref_block = c->opt_ref_block;
+    const int snap_warps = 8;
+    for (int32_t l = s.n_levels; l >= 1; --l) {
+      const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
+      if (n <= 0) continue;
+      reverse_snapshot_kernel<<<dim3(unsigned((n + snap_warps - 1) / snap_warps), unsigned(A.n_colblocks)),
+                                snap_warps * 32, 0, s.stream>>>(s.sched_lhs.as<int32_t>(), j0, n, g,
+                                                                 s.abuf.as<double>(), K, n_dirs);
+      s.launches += 1;
+      const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
+      if (c1 > c0) {
+        B.first_chunk = c0;
+        if (c->opt_time_kernels) RET(mark(s));
+        reverse_target_kernel<<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(B);
+        if (c->opt_time_kernels) RET(mark(s));
+        s.launches += 1;
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Enqueue (no host synchronisation) directions [d_lo, d_hi) of the Jacobian on one shard;
+// results go to `out` (device memory of this shard) as out[i*stride_i + (d - d_base)*stride_d],
+// i over the non-swept variable list.  shard_finish() waits and collects the timings.
+int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* seed_slots_dev,
+                  const int32_t* out_slots_dev, int64_t n_out, int64_t d_lo, int64_t d_hi, int64_t d_base,
+                  double* out, int64_t stride_i, int64_t stride_d) {
+  std::string* errp = &s.err;
+  CK(cudaSetDevice(s.dev));
+  const int64_t D = d_hi - d_lo;
+  s.kev_used = 0;
+  CK(cudaEventRecord(s.ev[0], s.stream));
+  CK(cudaEventRecord(s.ev[2], s.stream));
+  CK(cudaEventRecord(s.ev[3], s.stream));
+  s.stat["n_passes"] = 0;
+  if (D > 0) {
+    // pass size from the workspace budget
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget =
+        c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes) : size_t(double(free_b + s.g.bytes + s.abuf.bytes) * 0.6);
+    // per direction: a gradient column plus (reverse, level schedule) a column of the a-snapshot buffer
+    int64_t max_dirs = int64_t(budget / (size_t(s.max_gradient + s.max_step_width) * 8));
+    max_dirs = (max_dirs / 32) * 32;
+    if (max_dirs < 32) max_dirs = 32;
+    int64_t pass = std::min<int64_t>(((D + 31) / 32) * 32, max_dirs);
+    if (c->opt_pass_dirs > 0) pass = std::min<int64_t>(pass, ((c->opt_pass_dirs + 31) / 32) * 32);
+    const int64_t K = pass;
+    RET(ensure(errp, s.g, size_t(s.max_gradient) * size_t(K) * 8));
+    double* g = s.g.as<double>();
+    int n_passes = 0;
+    const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
+    if (plan.use_levels && mode == 1) RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
+    for (int64_t d0 = d_lo; d0 < d_hi; d0 += pass) {
+      const int64_t n = std::min(pass, d_hi - d0);
+      const bool last = d0 + pass >= d_hi;
+      CK(cudaMemsetAsync(g, 0, size_t(s.max_gradient) * size_t(K) * 8, s.stream));
+      seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n));
+      s.launches += 1;
+      if (last) CK(cudaEventRecord(s.ev[2], s.stream));
+      RET(launch_sweep(c, s, mode, g, K, n, plan));
+      if (last) CK(cudaEventRecord(s.ev[3], s.stream));
+      const dim3 eg(unsigned((n + 31) / 32), unsigned((n_out + 31) / 32));
+      extract_kernel<<<eg, dim3(32, 8), 0, s.stream>>>(g, K, out_slots_dev, n_out, int(n), d0 - d_base, out,
+                                                        stride_i, stride_d);
+      s.launches += 1;
+      ++n_passes;
+    }
+    s.stat["pass_dirs"] = double(pass);
+    s.stat["n_passes"] = double(n_passes);
+    s.stat["used_schedule"] = plan.use_levels ? 2.0 : 1.0;
+    s.stat["warps_per_cta"] = double(plan.warps);
+  }
+  CK(cudaEventRecord(s.ev[1], s.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int shard_finish(Shard& s) {
+  std::string* errp = &s.err;
+  CK(cudaSetDevice(s.dev));
+  CK(cudaStreamSynchronize(s.stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+  s.stat["replay_ms"] = ms;                       // zero-fill + seed + sweep + extraction, all passes
+  CK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
+  s.stat["sweep_ms"] = ms;                        // the replay kernels of the LAST pass alone
+  // dominant kernel (forward: replay_forward_kernel, reverse: reverse_target_kernel / replay_reverse_kernel),
+  // every launch timed on its own when "time_kernels" is on
+  double dom = 0;
+  for (size_t k = 0; k + 1 < s.kev_used; k += 2) {
+    CK(cudaEventElapsedTime(&ms, s.kev[k], s.kev[k + 1]));
+    dom += ms;
+  }
+  s.stat["dominant_ms"] = dom;
+  s.stat["dominant_launches"] = double(s.kev_used / 2);
+  return 0;
+}
+
+// Run fn(shard index) for every local shard: inline for one shard, one host thread per shard
+// otherwise (thousands of per-level launches per GPU must not be serialised behind each other).
+template <class F>
+int over_shards(adept_cuda_ctx* c, F fn) {
+  const size_t n = c->sh.size();
+  std::vector<int> rc(n, 0);
+  if (n == 1) {
+    rc[0] = fn(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < n; ++k) th.emplace_back([&, k]() { rc[k] = fn(k); });
+    for (std::thread& t : th) t.join();
+  }
+  for (size_t k = 0; k < n; ++k)
+    if (rc[k]) {
+      c->err = c->sh[k].err;
+      return rc[k];
+    }
+  return 0;
+}
+
+// strided re-layout on the root: dst[i*si + d*sd] = src[d*n_out + i]
+__global__ void relayout_kernel(const double* __restrict__ src, int64_t n_out, int64_t n_dirs, double* __restrict__ dst,
+                                int64_t si, int64_t sd) {
+  __shared__ double tile[32][33];
+  const int64_t i0 = int64_t(blockIdx.x) * 32, d0 = int64_t(blockIdx.y) * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t d = d0 + r, i = i0 + threadIdx.x;
+    if (d < n_dirs && i < n_out) tile[r][threadIdx.x] = src[d * n_out + i];
+  }
+  __syncthreads();
+  if (si <= sd) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int64_t d = d0 + r, i = i0 + threadIdx.x;
+      if (d < n_dirs && i < n_out) dst[i * si + d * sd] = tile[r][threadIdx.x];
+    }
+  } else {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int64_t d = d0 + threadIdx.x, i = i0 + r;
+      if (d < n_dirs && i < n_out) dst[i * si + d * sd] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+// host-side scatter of a direction-major block in the reference's write order (direction
+// blocks of P, then out index, then lane): only matters when user strides make elements overlap
+void scatter_host(const std::vector<double>& dm, int64_t D, int64_t n_out, double* out, int64_t stride_i,
+                  int64_t stride_d, int64_t P) {
+  for (int64_t d0 = 0; d0 < D; d0 += P)
+    for (int64_t i = 0; i < n_out; ++i)
+      for (int64_t d = d0; d < std::min(D, d0 + P); ++d) out[i * stride_i + d * stride_d] = dm[size_t(d) * n_out + i];
+}
+
+int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_indep, const int32_t* dep,
+                int64_t n_dep, double* jac_out, bool out_on_device, int64_t dep_offset, int64_t indep_offset) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  if (mode != ADEPT_CUDA_FORWARD && mode != ADEPT_CUDA_REVERSE) return fail(errp, ADEPT_CUDA_ERR_ARG, "mode must be 0 or 1");
+  Shard& root = c->sh[0];
+  if (!root.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
+  // reference pre-check (adept/jacobian.cpp:208-210, :466-468)
+  if (n_indep <= 0 || n_dep <= 0)
+    return fail(errp, ADEPT_CUDA_ERR_NOT_IDENTIFIED, "dependent or independent variables not identified");
+  if (!indep || !dep) return fail(errp, ADEPT_CUDA_ERR_ARG, "null index list");
+  const bool is_root_proc = (c->rank0 == 0);
+  if (is_root_proc && !jac_out) return fail(errp, ADEPT_CUDA_ERR_ARG, "null output");
+  for (int64_t i = 0; i < n_indep; ++i)
+    if (indep[i] < 0 || indep[i] >= root.max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "independent slot out of range");
+  for (int64_t i = 0; i < n_dep; ++i)
+    if (dep[i] < 0 || dep[i] >= root.max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "dependent slot out of range");
+  // offset defaulting exactly as adept/jacobian.cpp:215-220
+  if (dep_offset <= 0) dep_offset = n_indep;
+  if (indep_offset <= 0) indep_offset = n_dep;
+
+  const int64_t D = (mode == 0) ? n_indep : n_dep;          // directions
+  const int64_t n_out = (mode == 0) ? n_dep : n_indep;      // entries per direction
+  const int32_t* seeds = (mode == 0) ? indep : dep;
+  const int32_t* outs = (mode == 0) ? dep : indep;
+  const int64_t stride_i = (mode == 0) ? dep_offset : indep_offset;  // user stride of the out-list index
+  const int64_t stride_d = (mode == 0) ? indep_offset : dep_offset;  // user stride of the direction index
+
+  // direction partition over all ranks, in multiples of 32 (keeps the reference's P-blocks whole)
+  const int W = c->world;
+  int64_t blk = (D + W - 1) / W;
+  blk = ((blk + 31) / 32) * 32;
+  auto lo_of = [&](int r) { return std::min<int64_t>(D, int64_t(r) * blk); };
+
+  auto t_begin = std::chrono::steady_clock::now();
+  // index lists to every local shard
+  for (Shard& s : c->sh) {
+    CK(cudaSetDevice(s.dev));
+    RET(ensure(errp, s.seed_slots, size_t(D) * 4));
+    RET(ensure(errp, s.out_slots, size_t(n_out) * 4));
+    CK(cudaMemcpyAsync(s.seed_slots.p, seeds, size_t(D) * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.out_slots.p, outs, size_t(n_out) * 4, cudaMemcpyHostToDevice, s.stream));
+  }
+
+  const bool compact_user = (stride_i == 1 && stride_d == n_out) || (stride_d == 1 && stride_i == D);
+  const bool dm_is_final = (stride_i == 1 && stride_d == n_out);
+  if (W == 1) {
+    // single GPU: extract straight into the final layout
+    Shard& s = root;
+    double* dev_out = nullptr;
+    int64_t si = stride_i, sd = stride_d;
+    if (out_on_device) {
+      dev_out = jac_out;
+    } else {
+      RET(ensure(errp, s.out, size_t(D) * size_t(n_out) * 8));
+      dev_out = s.out.as<double>();
+      if (!compact_user) { si = 1; sd = n_out; }
+    }
+    int rc = shard_enqueue(c, s, mode, s.seed_slots.as<int32_t>(), s.out_slots.as<int32_t>(), n_out, 0, D, 0, dev_out, si, sd);
+    if (!rc) rc = shard_finish(s);
+    if (rc) { c->err = s.err; return rc; }
+    if (!out_on_device) {
+      auto t0 = std::chrono::steady_clock::now();
+      if (compact_user) {
+        CK(cudaMemcpyAsync(jac_out, dev_out, size_t(D) * size_t(n_out) * 8, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+      } else {
+        std::vector<double> tmp(size_t(D) * size_t(n_out));
+        CK(cudaMemcpyAsync(tmp.data(), dev_out, tmp.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        scatter_host(tmp, D, n_out, jac_out, stride_i, stride_d, c->opt_ref_block);
+      }
+      c->stat["d2h_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  } else {
+    // multi GPU: every rank fills a direction-major block dm[(d-lo)*n_out + i]; the blocks are
+    // gathered on global rank 0 (ncclSend/ncclRecv over NVLink) and re-laid out there.
+    RET(over_shards(c, [&](size_t k) -> int {
+      Shard& s = c->sh[k];
+      std::string* errp = &s.err;
+      const int r = c->rank0 + int(k);
+      const int64_t lo = lo_of(r), hi = lo_of(r + 1);
+      CK(cudaSetDevice(s.dev));
+      const bool is_root = (r == 0);
+      RET(ensure(errp, s.out, size_t(is_root ? D : std::max<int64_t>(hi - lo, 1)) * size_t(n_out) * 8));
+      return shard_enqueue(c, s, mode, s.seed_slots.as<int32_t>(), s.out_slots.as<int32_t>(), n_out, lo, hi,
+                           is_root ? 0 : lo, s.out.as<double>(), 1, n_out);
+    }));
+    NK(ncclGroupStart());
+    for (size_t k = 0; k < c->sh.size(); ++k) {
+      Shard& s = c->sh[k];
+      const int r = c->rank0 + int(k);
+      if (r == 0) {
+        for (int q = 1; q < W; ++q) {
+          const int64_t lo = lo_of(q), hi = lo_of(q + 1);
+          if (hi > lo) NK(ncclRecv(s.out.as<double>() + lo * n_out, size_t(hi - lo) * n_out, ncclDouble, q, s.comm, s.stream));
+        }
+      } else {
+        const int64_t lo = lo_of(r), hi = lo_of(r + 1);
+        if (hi > lo) NK(ncclSend(s.out.as<double>(), size_t(hi - lo) * n_out, ncclDouble, 0, s.comm, s.stream));
+      }
+    }
+    NK(ncclGroupEnd());
+    RET(over_shards(c, [&](size_t k) -> int { return shard_finish(c->sh[k]); }));
+    if (is_root_proc) {
+      Shard& s = root;
+      CK(cudaSetDevice(s.dev));
+      auto t0 = std::chrono::steady_clock::now();
+      double* final_dev = s.out.as<double>();
+      if (out_on_device) {
+        if (dm_is_final) {
+          CK(cudaMemcpyAsync(jac_out, s.out.p, size_t(D) * n_out * 8, cudaMemcpyDeviceToDevice, s.stream));
+        } else {
+          const dim3 g(unsigned((n_out + 31) / 32), unsigned((D + 31) / 32));
+          relayout_kernel<<<g, dim3(32, 8), 0, s.stream>>>(s.out.as<double>(), n_out, D, jac_out, stride_i, stride_d);
+          s.launches += 1;
+        }
+        CK(cudaStreamSynchronize(s.stream));
+      } else {
+        if (!dm_is_final && compact_user) {
+          RET(ensure(errp, s.scratch, size_t(D) * n_out * 8));
+          const dim3 g(unsigned((n_out + 31) / 32), unsigned((D + 31) / 32));
+          relayout_kernel<<<g, dim3(32, 8), 0, s.stream>>>(s.out.as<double>(), n_out, D, s.scratch.as<double>(),
+                                                           stride_i, stride_d);
+          s.launches += 1;
+          final_dev = s.scratch.as<double>();
+        }
+        if (dm_is_final || compact_user) {
+          CK(cudaMemcpyAsync(jac_out, final_dev, size_t(D) * n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+          CK(cudaStreamSynchronize(s.stream));
+        } else {
+          std::vector<double> tmp(size_t(D) * size_t(n_out));
+          CK(cudaMemcpyAsync(tmp.data(), s.out.p, tmp.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+          CK(cudaStreamSynchronize(s.stream));
+          scatter_host(tmp, D, n_out, jac_out, stride_i, stride_d, c->opt_ref_block);
+        }
+      }
+      c->stat["d2h_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  }
+  // this process's view: the slowest local shard
+  double replay_ms = 0, sweep_ms = 0;
+  for (Shard& s : c->sh) {
+    replay_ms = std::max(replay_ms, s.stat["replay_ms"]);
+    sweep_ms = std::max(sweep_ms, s.stat["sweep_ms"]);
+  }
+  for (const auto& kv : root.stat) c->stat[kv.first] = kv.second;
+  c->stat["replay_ms"] = replay_ms;
+  c->stat["sweep_ms"] = sweep_ms;
+  c->stat["jacobian_wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  c->stat["kernel_launches"] = c->total_launches();
+  return 0;
+}
+
+
+// single-direction sweep on shard 0: gradient vector in/out on the host
+int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initialized, int flags) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  Shard& s = c->sh[0];
+  if (!initialized) return fail(errp, ADEPT_CUDA_ERR_GRAD_NOT_INIT, "gradients not initialized");
+  if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
+  if (!gradient_host) return fail(errp, ADEPT_CUDA_ERR_ARG, "null gradient vector");
+  CK(cudaSetDevice(s.dev));
+  const int64_t G = s.max_gradient;
+  RET(ensure(errp, s.g1, size_t(G) * 8));
+  double* g = s.g1.as<double>();
+  if (int rc = upload(s, g, gradient_host, size_t(G) * 8)) { c->err = s.err; return rc; }
+  CK(cudaEventRecord(s.ev[0], s.stream));
+  const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
+  if (s.R > 0) {
+    if (ordered) {
+      ReplayArgs A;
+      A.g = g;
+      A.K = 1;
+      A.n_colblocks = 1;
+      A.n_dirs = 1;  // K = 1: lanes 1..31 are masked off
+      A.ref_block = 1;
+      A.recs = (adjoint ? s.rev_t : s.fwd_t).as<Rec>();
+      A.chunk_begin = s.one_chunk.as<int64_t>();
+      A.first_chunk = 0;
+      if (adjoint) replay_reverse_kernel<<<dim3(1, 1), 32, 0, s.stream>>>(A);
+      else replay_forward_kernel<true><<<dim3(1, 1), 32, 0, s.stream>>>(A);
+      s.launches += 1;
+    } else {
+      const Rec* recs = s.fwd_l.as<Rec>();
+      const int64_t* foff = s.foff.as<int64_t>();
+      if (!adjoint) {
+        size_t lf = 0;  // cursor into long_stmts (sorted by schedule position, hence by step)
+        for (int32_t l = 1; l <= s.n_levels; ++l) {
+          const int64_t j0 = s.level_first[l], j1 = s.level_first[l + 1];
+          if (j1 > j0) {
+            sweep1_forward_level_kernel<<<unsigned((j1 - j0 + 255) / 256), 256, 0, s.stream>>>(recs, foff, j0, j1,
+                                                                                               kLongThreshold, g);
+            s.launches += 1;
+          }
+          while (lf < s.long_stmts.size() && s.long_stmts[lf].level == l) {
+            const LongStmt& L = s.long_stmts[lf++];
+            sweep1_forward_long_kernel<<<1, 512, 0, s.stream>>>(recs, L.b, L.e, g);
+            s.launches += 1;
+          }
+        }
+      } else {
+        RET(ensure(errp, s.a1, size_t(std::max<int64_t>(s.max_step_width, 1)) * 8));
+        for (int32_t l = s.n_levels; l >= 1; --l) {
+          const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
+          if (n <= 0) continue;
+          sweep1_snapshot_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(s.sched_lhs.as<int32_t>(), j0, n, g,
+                                                                                  s.a1.as<double>());
+          s.launches += 1;
+          const int64_t g0 = s.step_group[l], g1 = s.step_group[l + 1];
+          if (g1 > g0) {
+            sweep1_target_kernel<<<unsigned((g1 - g0 + 255) / 256), 256, 0, s.stream>>>(
+                s.tgt.as<Rec>(), s.goff.as<int64_t>(), g0, g1, g, s.a1.as<double>());
+            s.launches += 1;
+          }
+        }
+      }
+    }
+  }
+  CK(cudaEventRecord(s.ev[1], s.stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(gradient_host, g, size_t(G) * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+  c->stat["replay_ms"] = ms;
+  c->stat["sweep_ms"] = ms;
+  c->stat["used_schedule"] = ordered ? 1.0 : 2.0;
+  c->stat["kernel_launches"] = c->total_launches();
+  return 0;
+}
+
+int init_shard(Shard& s, int dev) {
+  std::string* errp = &s.err;
+  s.dev = dev;
+  CK(cudaSetDevice(dev));
+  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&s.ev[k]));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  s.sm_count = prop.multiProcessorCount;
+  if (prop.major < 10)
+    return fail(errp, ADEPT_CUDA_ERR_CUDA, "device %d is sm_%d%d; libadept_cuda is built for sm_100a only", dev, prop.major,
+                prop.minor);
+  return 0;
+}
+
+void free_shard(Shard& s) {
+  cudaSetDevice(s.dev);
+  for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.abuf, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+    release(*b);
+  for (int k = 0; k < 2; ++k) {
+    if (s.stage[k]) cudaFreeHost(s.stage[k]);
+    if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
+  }
+  for (int k = 0; k < 4; ++k)
+    if (s.ev[k]) cudaEventDestroy(s.ev[k]);
+  for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
+  if (s.comm) ncclCommDestroy(s.comm);
+  if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* adept_cuda_version(void) { return "adept-2_b200 0.1 (sm_100a)"; }
+
+const char* adept_cuda_last_error(const adept_cuda_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int adept_cuda_create(adept_cuda_ctx** out, const int* devices, int n_devices) {
+  if (!out || n_devices < 1) return ADEPT_CUDA_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1) return ADEPT_CUDA_ERR_CUDA;  // no CPU fallback by design
+  adept_cuda_ctx* c = new adept_cuda_ctx();
+  c->sh.resize(n_devices);
+  for (int k = 0; k < n_devices; ++k) {
+    const int dev = devices ? devices[k] : k;
+    if (dev < 0 || dev >= count) { delete c; return ADEPT_CUDA_ERR_ARG; }
+    int rc = init_shard(c->sh[k], dev);
+    if (rc) {
+      fprintf(stderr, "adept_cuda_create: %s\n", c->sh[k].err.c_str());
+      for (Shard& s : c->sh) free_shard(s);
+      delete c;
+      return rc;
+    }
+  }
+  c->world = n_devices;
+  c->rank0 = 0;
+  if (n_devices > 1) {
+    std::vector<ncclComm_t> comms(n_devices);
+    std::vector<int> devs(n_devices);
+    for (int k = 0; k < n_devices; ++k) devs[k] = c->sh[k].dev;
+    ncclResult_t r = ncclCommInitAll(comms.data(), n_devices, devs.data());
+    if (r != ncclSuccess) {
+      fprintf(stderr, "adept_cuda_create: ncclCommInitAll failed: %s\n", ncclGetErrorString(r));
+      for (Shard& s : c->sh) free_shard(s);
+      delete c;
+      return ADEPT_CUDA_ERR_NCCL;
+    }
+    for (int k = 0; k < n_devices; ++k) c->sh[k].comm = comms[k];
+  }
+  *out = c;
+  return 0;
+}
+
+void adept_cuda_destroy(adept_cuda_ctx* c) {
+  if (!c) return;
+  for (Shard& s : c->sh) free_shard(s);
+  delete c;
+}
+
+int adept_cuda_unique_id(void* id128) {
+  if (!id128) return ADEPT_CUDA_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return ADEPT_CUDA_ERR_NCCL;
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+
+int adept_cuda_join(adept_cuda_ctx* c, const void* id128, int rank, int world_size) {
+  if (!c || !id128 || rank < 0 || rank >= world_size) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  if (c->sh.size() != 1) return fail(errp, ADEPT_CUDA_ERR_ARG, "adept_cuda_join needs a one-device context");
+  Shard& s = c->sh[0];
+  CK(cudaSetDevice(s.dev));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  if (s.comm) { ncclCommDestroy(s.comm); s.comm = nullptr; }
+  NK(ncclCommInitRank(&s.comm, world_size, id, rank));
+  c->world = world_size;
+  c->rank0 = rank;
+  c->multi_process = true;
+  return 0;
+}
+
+int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_stmt, const double* multiplier,
+                           const int32_t* index, int64_t n_ops, int64_t max_gradient, uint64_t epoch) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  if (!statements || n_stmt < 1 || n_ops < 0 || max_gradient < 1 || (n_ops > 0 && (!multiplier || !index)))
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "bad tape arguments");
+  if (max_gradient >= (int64_t(1) << 31)) return fail(errp, ADEPT_CUDA_ERR_LIMIT, "max_gradient >= 2^31");
+  Shard& s = c->sh[0];
+  CK(cudaSetDevice(s.dev));
+  auto t0 = std::chrono::steady_clock::now();
+  s.have_tape = false;
+  RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
+  RET(ensure(errp, s.mult, size_t(n_ops) * 8));
+  RET(ensure(errp, s.idx, size_t(n_ops) * 4));
+  {
+    int rc = upload(s, s.stmt.p, statements, size_t(n_stmt) * 8);
+    if (!rc) rc = upload(s, s.mult.p, multiplier, size_t(n_ops) * 8);
+    if (!rc) rc = upload(s, s.idx.p, index, size_t(n_ops) * 4);
+    if (rc) { c->err = s.err; return rc; }
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  s.n_stmt = n_stmt;
+  s.n_ops = n_ops;
+  s.max_gradient = max_gradient;
+  auto t1 = std::chrono::steady_clock::now();
+  c->stat["upload_ms"] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  // single-process multi-GPU: broadcast right away
+  if (!c->multi_process && c->sh.size() > 1) {
+    for (size_t k = 1; k < c->sh.size(); ++k) {
+      Shard& d = c->sh[k];
+      CK(cudaSetDevice(d.dev));
+      RET(ensure(errp, d.stmt, size_t(n_stmt) * 8));
+      RET(ensure(errp, d.mult, size_t(n_ops) * 8));
+      RET(ensure(errp, d.idx, size_t(n_ops) * 4));
+      d.n_stmt = n_stmt; d.n_ops = n_ops; d.max_gradient = max_gradient;
+    }
+    NK(ncclGroupStart());
+    for (Shard& d : c->sh) {
+      NK(ncclBroadcast(d.stmt.p, d.stmt.p, size_t(n_stmt) * 8, ncclChar, 0, d.comm, d.stream));
+      NK(ncclBroadcast(d.mult.p, d.mult.p, size_t(n_ops) * 8, ncclChar, 0, d.comm, d.stream));
+      NK(ncclBroadcast(d.idx.p, d.idx.p, size_t(n_ops) * 4, ncclChar, 0, d.comm, d.stream));
+    }
+    NK(ncclGroupEnd());
+    for (Shard& d : c->sh) { CK(cudaSetDevice(d.dev)); CK(cudaStreamSynchronize(d.stream)); }
+    c->stat["bcast_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+  }
+  auto t2 = std::chrono::steady_clock::now();
+  RET(over_shards(c, [&](size_t k) -> int {
+    Shard& d = c->sh[k];
+    std::string* errp = &d.err;
+    RET(build_schedule(c, d));
+    CK(cudaStreamSynchronize(d.stream));
+    d.have_tape = true;
+    return 0;
+  }));
+  c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
+  c->stat["n_levels"] = s.n_levels;
+  c->stat["n_chunks"] = double(s.n_chunks);
+  c->stat["n_records"] = double(s.R);
+  c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
+  c->stat["kernel_launches"] = c->total_launches();
+  c->epoch = epoch;
+  return 0;
+}
+
+int adept_cuda_share_tape(adept_cuda_ctx* c, int root_rank) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  if (!c->multi_process) return 0;  // single-process contexts broadcast inside upload_tape
+  Shard& s = c->sh[0];
+  CK(cudaSetDevice(s.dev));
+  auto t0 = std::chrono::steady_clock::now();
+  RET(ensure(errp, s.scratch, 64));
+  int64_t hdr[4] = {s.n_stmt, s.n_ops, s.max_gradient, int64_t(c->epoch)};
+  if (c->rank0 == root_rank) {
+    if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "root has no tape to share");
+    CK(cudaMemcpyAsync(s.scratch.p, hdr, sizeof hdr, cudaMemcpyHostToDevice, s.stream));
+  }
+  NK(ncclBroadcast(s.scratch.p, s.scratch.p, sizeof hdr, ncclChar, root_rank, s.comm, s.stream));
+  CK(cudaMemcpyAsync(hdr, s.scratch.p, sizeof hdr, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  if (c->rank0 != root_rank) {
+    s.have_tape = false;
+    s.n_stmt = hdr[0]; s.n_ops = hdr[1]; s.max_gradient = hdr[2]; c->epoch = uint64_t(hdr[3]);
+    RET(ensure(errp, s.stmt, size_t(s.n_stmt) * 8));
+    RET(ensure(errp, s.mult, size_t(s.n_ops) * 8));
+    RET(ensure(errp, s.idx, size_t(s.n_ops) * 4));
+  }
+  NK(ncclGroupStart());
+  NK(ncclBroadcast(s.stmt.p, s.stmt.p, size_t(s.n_stmt) * 8, ncclChar, root_rank, s.comm, s.stream));
+  NK(ncclBroadcast(s.mult.p, s.mult.p, size_t(s.n_ops) * 8, ncclChar, root_rank, s.comm, s.stream));
+  NK(ncclBroadcast(s.idx.p, s.idx.p, size_t(s.n_ops) * 4, ncclChar, root_rank, s.comm, s.stream));
+  NK(ncclGroupEnd());
+  CK(cudaStreamSynchronize(s.stream));
+  c->stat["bcast_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (c->rank0 != root_rank) {
+    auto t2 = std::chrono::steady_clock::now();
+    if (int rc = build_schedule(c, s)) { c->err = s.err; return rc; }
+    CK(cudaStreamSynchronize(s.stream));
+    s.have_tape = true;
+    c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
+    c->stat["n_levels"] = s.n_levels;
+    c->stat["n_chunks"] = double(s.n_chunks);
+    c->stat["n_records"] = double(s.R);
+    c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
+  }
+  return 0;
+}
+
+int adept_cuda_tape_epoch(const adept_cuda_ctx* c, uint64_t* epoch, int64_t* n_stmt, int64_t* n_ops) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  if (!c->sh[0].have_tape) return ADEPT_CUDA_ERR_NO_TAPE;
+  if (epoch) *epoch = c->epoch;
+  if (n_stmt) *n_stmt = c->sh[0].n_stmt;
+  if (n_ops) *n_ops = c->sh[0].n_ops;
+  return 0;
+}
+
+int adept_cuda_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_indep, const int32_t* dep,
+                        int64_t n_dep, double* jac_out_host, int64_t dep_offset, int64_t indep_offset) {
+  return do_jacobian(c, mode, indep, n_indep, dep, n_dep, jac_out_host, false, dep_offset, indep_offset);
+}
+
+int adept_cuda_jacobian_device(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_indep, const int32_t* dep,
+                               int64_t n_dep, double* jac_out_device, int64_t dep_offset, int64_t indep_offset) {
+  return do_jacobian(c, mode, indep, n_indep, dep, n_dep, jac_out_device, true, dep_offset, indep_offset);
+}
+
+int adept_cuda_tangent_linear(adept_cuda_ctx* c, double* gradient_host, int initialized, int flags) {
+  return do_sweep1(c, 0, gradient_host, initialized, flags);
+}
+
+int adept_cuda_adjoint(adept_cuda_ctx* c, double* gradient_host, int initialized, int flags) {
+  return do_sweep1(c, 1, gradient_host, initialized, flags);
+}
+
+int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statements, int64_t n_stmt,
+                              const int32_t* index, int64_t n_ops, int64_t max_gradient, const double* multipliers,
+                              int64_t n_members, const int32_t* indep, int64_t n_indep, const int32_t* dep,
+                              int64_t n_dep, double* jac_out_host) {
+  (void)mode; (void)statements; (void)n_stmt; (void)index; (void)n_ops; (void)max_gradient; (void)multipliers;
+  (void)n_members; (void)indep; (void)n_indep; (void)dep; (void)n_dep; (void)jac_out_host;
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  return fail(errp, ADEPT_CUDA_ERR_ARG, "adept_cuda_jacobian_batch: not built yet");
+}
+
+int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  const std::string k(key);
+  if (k == "schedule") {
+    if (value < 0 || value > 2) return fail(errp, ADEPT_CUDA_ERR_ARG, "schedule must be 0, 1 or 2");
+    c->opt_schedule = int(value);
+  } else if (k == "ref_block") {
+    if (value < 1 || value > 32 || (value & (value - 1))) return fail(errp, ADEPT_CUDA_ERR_ARG, "ref_block must be a power of two <= 32");
+    c->opt_ref_block = int(value);
+  } else if (k == "pass_dirs") {
+    if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "pass_dirs must be >= 0");
+    c->opt_pass_dirs = value;
+  } else if (k == "workspace_bytes") {
+    if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
+    c->opt_workspace_bytes = value;
+  } else if (k == "time_kernels") {
+    c->opt_time_kernels = value ? 1 : 0;
+  } else if (k == "window") {
+    if (value < 0 || (value > 0 && value < 32)) return fail(errp, ADEPT_CUDA_ERR_ARG, "window must be 0 (default) or >= 32");
+    c->opt_window = value;
+  } else if (k == "warps_per_cta") {
+    if (value < 1 || value > 8) return fail(errp, ADEPT_CUDA_ERR_ARG, "warps_per_cta must be in 1..8");
+    c->opt_warps = int(value);
+  } else {
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "unknown option '%s'", key);
+  }
+  return 0;
+}
+
+int adept_cuda_get_stat(const adept_cuda_ctx* c, const char* key, double* value) {
+  if (!c || !key || !value) return ADEPT_CUDA_ERR_ARG;
+  auto it = c->stat.find(key);
+  if (it == c->stat.end()) return ADEPT_CUDA_ERR_ARG;
+  *value = it->second;
+  return 0;
+}
+
+int adept_cuda_get_levels(adept_cuda_ctx* c, int32_t* level_out, int64_t n_stmt) {
+  if (!c || !level_out) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  Shard& s = c->sh[0];
+  if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
+  if (!s.have_levels) return fail(errp, ADEPT_CUDA_ERR_ARG, "no level schedule was built for this tape");
+  if (n_stmt != s.n_stmt) return fail(errp, ADEPT_CUDA_ERR_ARG, "n_stmt mismatch");
+  CK(cudaSetDevice(s.dev));
+  CK(cudaMemcpy(level_out, s.level.p, size_t(n_stmt) * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

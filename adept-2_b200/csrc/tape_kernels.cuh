@@ -1,0 +1,441 @@
+// tape_kernels.cuh -- device-side tape preparation: validation, linearisation into record
+// streams, dependency analysis (levels) and level-major re-emission.
+//
+// Input is the reference's tape exactly as recorded (include/adept/Statement.h:24-30,
+// include/adept/StackStorageOrig.h:155-163): stmt[s] = {lhs slot, end_plus_one} with the
+// {-1,0} sentinel at s = 0; statement s >= 1 owns operations [stmt[s-1].end, stmt[s].end).
+//
+// Notation: S = n_stmt-1 real statements, O = n_ops, R = O + S records.
+//   forward tape-order position of op o of statement s : o + (s-1)
+//   forward tape-order position of the TAIL of s       : end[s] + (s-1)
+//   reverse tape-order base of s (its HEAD)            : (S-s) + (O-end[s]); op o follows at
+//                                                        base + 1 + (o - end[s-1])
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace adept_b200 {
+namespace cg = cooperative_groups;
+
+// statement (>= 1) that owns operation o: smallest s with end[s] > o
+__device__ __forceinline__ int64_t stmt_of_op(const int2* __restrict__ stmt, int64_t n_stmt, int64_t o) {
+  int64_t lo = 1, hi = n_stmt - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (static_cast<int64_t>(stmt[mid].y) > o) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+
+// flags[0] |= 1 on any malformed entry (slot out of range, ends not monotone).
+__global__ void validate_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ idx,
+                                int64_t n_ops, int64_t max_gradient, int* flags) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  bool bad = false;
+  for (int64_t o = t; o < n_ops; o += stride) {
+    const int32_t x = idx[o];
+    if (x < 0 || x >= max_gradient) bad = true;
+  }
+  for (int64_t s = t; s < n_stmt; s += stride) {
+    const int2 st = stmt[s];
+    if (s == 0) {
+      if (st.y != 0) bad = true;
+    } else {
+      if (st.x < 0 || st.x >= max_gradient) bad = true;
+      if (st.y < stmt[s - 1].y || st.y > n_ops) bad = true;
+      if (s == n_stmt - 1 && st.y != n_ops) bad = true;
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
+// Tape-order streams.  One thread per record of the forward stream.
+__global__ void build_streams_kernel(const int2* __restrict__ stmt, int64_t n_stmt,
+                                     const double* __restrict__ mult, const int32_t* __restrict__ idx,
+                                     int64_t n_ops, Rec* __restrict__ fwd, Rec* __restrict__ rev,
+                                     int32_t* __restrict__ rec_stmt) {
+  const int64_t S = n_stmt - 1;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = t; o < n_ops; o += stride) {
+    const int64_t s = stmt_of_op(stmt, n_stmt, o);
+    Rec r;
+    r.m = mult[o];
+    r.slot = idx[o];
+    r.kind = REC_OP;
+    const int64_t fpos = o + (s - 1);
+    fwd[fpos] = r;
+    if (rec_stmt) rec_stmt[fpos] = static_cast<int32_t>(s);
+    const int64_t base = (S - s) + (n_ops - stmt[s].y);
+    rev[base + 1 + (o - stmt[s - 1].y)] = r;
+  }
+  for (int64_t s = 1 + t; s < n_stmt; s += stride) {
+    Rec r;
+    r.m = 0.0;
+    r.slot = stmt[s].x;
+    r.kind = REC_MARK;
+    const int64_t fpos = static_cast<int64_t>(stmt[s].y) + (s - 1);
+    fwd[fpos] = r;
+    if (rec_stmt) rec_stmt[fpos] = static_cast<int32_t>(s);
+    rev[(S - s) + (n_ops - stmt[s].y)] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Dependency analysis (no counterpart in the reference, which replays strictly in tape order).
+//
+// A statement may leave its tape position as long as no bit of any sweep changes.  That holds
+// under these constraints on the step number of each statement (oracle/replay_oracle.c,
+// oracle_levels mode 2, is the sequential statement of the same rule):
+//   RAW  a reader of a slot version runs after its writer;
+//   WAR  the next writer of the slot runs after every reader of the old version;
+//   WAW  writers of a slot keep their order;
+//   MONO readers of one slot version have non-decreasing steps in tape order.
+// Forward sweeps are gathers (each statement adds its own operands in tape order), so RAW/WAR/
+// WAW suffice.  Reverse sweeps walk the steps downwards and, inside a step, add the
+// contributions to each slot in (statement descending, operand ascending) order (the "target
+// stream" below); MONO makes that the reference's accumulation order across steps too.
+//
+// The tape is cut into windows of `window` statements; ONE WARP analyses one window
+// sequentially (lanes share the operands of a statement), keeping per-slot (writer step,
+// max reader step) in an open-addressing hash table in global memory.  Steps are local to the
+// window; the global step is (window, local step) in lexicographic order.
+// ---------------------------------------------------------------------------------------
+struct __align__(16) SlotEntry {
+  int32_t key;  // slot, -1 = empty   (tables are memset to 0xFF: key = wl = rl = -1)
+  int32_t wl;   // step of the last writer   (<= 0: none in this window)
+  int32_t rl;   // max step of the readers of the current version (<= 0: none)
+  int32_t pad;
+};
+
+// capacity (power of two >= 2 * touches) of every window's table
+__global__ void window_caps_kernel(const int2* __restrict__ stmt, int64_t n_stmt, int64_t window, int64_t n_windows,
+                                   int64_t* __restrict__ cap) {
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w > n_windows) return;
+  if (w == n_windows) { cap[w] = 0; return; }
+  const int64_t S = n_stmt - 1;
+  const int64_t lo = 1 + w * window;
+  const int64_t hi = (lo + window - 1 < S) ? (lo + window - 1) : S;
+  const int64_t touches = (static_cast<int64_t>(stmt[hi].y) - stmt[lo - 1].y) + (hi - lo + 1);
+  int64_t c = 64;
+  while (c < 2 * touches) c <<= 1;
+  cap[w] = c;
+}
+
+__device__ __forceinline__ uint32_t slot_hash(int32_t x) {
+  uint32_t h = static_cast<uint32_t>(x) * 0x9E3779B1u;
+  return h ^ (h >> 15);
+}
+// find the entry of slot x, inserting it if absent
+__device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, int32_t x) {
+  uint32_t h = slot_hash(x) & mask;
+  while (true) {
+    const int32_t k = atomicCAS(&T[h].key, -1, x);
+    if (k == -1 || k == x) return &T[h];
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restrict__ stmt, int64_t n_stmt,
+                                                            const int32_t* __restrict__ idx, int64_t window,
+                                                            int64_t n_windows, SlotEntry* __restrict__ tables,
+                                                            const int64_t* __restrict__ tab_off,
+                                                            int32_t* __restrict__ level, int32_t* __restrict__ win_depth) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_windows) return;
+  const int64_t S = n_stmt - 1;
+  const int64_t lo = 1 + w * window;
+  const int64_t hi = (lo + window - 1 < S) ? (lo + window - 1) : S;
+  SlotEntry* T = tables + tab_off[w];
+  const uint32_t mask = static_cast<uint32_t>(tab_off[w + 1] - tab_off[w]) - 1u;
+  int32_t depth = 0;
+  int64_t o0 = stmt[lo - 1].y;
+  for (int64_t s = lo; s <= hi; ++s) {
+    const int2 st = stmt[s];
+    const int64_t o1 = st.y;
+    int32_t lv = 1;
+    for (int64_t o = o0 + lane; o < o1; o += 32) {
+      SlotEntry* e = table_entry(T, mask, idx[o]);
+      const int32_t wl = __ldcg(&e->wl), rl = __ldcg(&e->rl);
+      lv = max(lv, max(wl + 1, rl));       // RAW (strict), MONO (non-strict); empty = -1 -> 0, -1
+    }
+    SlotEntry* eL = table_entry(T, mask, st.x);
+    lv = max(lv, max(__ldcg(&eL->wl), __ldcg(&eL->rl)) + 1);  // WAW, WAR (strict)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+    __syncwarp();
+    for (int64_t o = o0 + lane; o < o1; o += 32) {
+      SlotEntry* e = table_entry(T, mask, idx[o]);
+      __stcg(&e->rl, lv);                   // lv >= the old rl by MONO
+    }
+    __syncwarp();
+    if (lane == 0) {                        // the write retires the old version and its readers
+      __stcg(&eL->wl, lv);
+      __stcg(&eL->rl, 0);
+      level[s] = lv;
+    }
+    __syncwarp();
+    depth = max(depth, lv);
+    o0 = o1;
+  }
+  if (lane == 0) win_depth[w] = depth;
+}
+
+// global step of every statement: step_base[window] + local level
+__global__ void global_steps_kernel(int32_t* __restrict__ level, int64_t n_stmt, int64_t window,
+                                    const int32_t* __restrict__ step_base) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = 1 + t; s < n_stmt; s += stride) level[s] += step_base[(s - 1) / window];
+  if (t == 0) level[0] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Level-major emission.
+// ---------------------------------------------------------------------------------------
+// keys for the stable sort of statements by level: key[j] = level[j+1], val[j] = j+1
+__global__ void level_keys_kernel(const int32_t* __restrict__ level, int64_t S, uint32_t* __restrict__ key,
+                                  uint32_t* __restrict__ val) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride) {
+    key[j] = static_cast<uint32_t>(level[j + 1]);
+    val[j] = static_cast<uint32_t>(j + 1);
+  }
+}
+
+// nrec[j] for the scheduled statement order; level_first[l] = first j of level l (1-based), and
+// level_first[n_levels+1] = S.
+__global__ void sched_sizes_kernel(const int2* __restrict__ stmt, const uint32_t* __restrict__ sched_stmt,
+                                   const uint32_t* __restrict__ sched_level, int64_t S, int32_t n_levels,
+                                   int64_t* __restrict__ nrec, int64_t* __restrict__ level_first) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride) {
+    const uint32_t s = sched_stmt[j];
+    nrec[j] = static_cast<int64_t>(stmt[s].y) - stmt[s - 1].y + 1;
+    if (j == 0 || sched_level[j] != sched_level[j - 1]) level_first[sched_level[j]] = j;
+  }
+  if (t == 0) {
+    level_first[0] = 0;
+    level_first[n_levels + 1] = S;
+  }
+}
+
+// chunk flags: statement j opens a chunk if it is the first of its level or crosses a
+// chunk_recs boundary of the stream.
+__global__ void chunk_flags_kernel(const int64_t* __restrict__ foff, const uint32_t* __restrict__ sched_level,
+                                   int64_t S, int64_t chunk_recs, int32_t* __restrict__ flag) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride) {
+    int f = 0;
+    if (j == 0 || sched_level[j] != sched_level[j - 1]) f = 1;
+    else if (foff[j] / chunk_recs != foff[j - 1] / chunk_recs) f = 1;
+    flag[j] = f;
+  }
+}
+
+// chunk tables: fwd_chunk[c] = foff[j] for the c-th flagged j; fwd_chunk[n_chunks] = R;
+// rev_chunk[c'] = R - fwd_chunk[n_chunks - c']; level_chunk[l] = chunk id of level_first[l].
+__global__ void chunk_tables_kernel(const int64_t* __restrict__ foff, const int32_t* __restrict__ flag,
+                                    const int32_t* __restrict__ chunk_id /* exclusive scan of flag */, int64_t S,
+                                    int64_t R, int64_t n_chunks, const int64_t* __restrict__ level_first,
+                                    int32_t n_levels, int64_t* __restrict__ fwd_chunk, int64_t* __restrict__ rev_chunk,
+                                    int64_t* __restrict__ level_chunk) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride) {
+    if (flag[j]) {
+      const int64_t c = chunk_id[j];
+      fwd_chunk[c] = foff[j];
+      if (rev_chunk) rev_chunk[n_chunks - c] = R - foff[j];
+    }
+  }
+  for (int64_t l = 1 + t; l <= n_levels; l += stride) level_chunk[l] = chunk_id[level_first[l]];
+  if (t == 0) {
+    fwd_chunk[n_chunks] = R;
+    if (rev_chunk) rev_chunk[0] = 0;
+    level_chunk[0] = 0;
+    level_chunk[n_levels + 1] = n_chunks;
+  }
+}
+
+// Level-major record streams.  One thread per destination record of the forward stream; the
+// mirrored record of the reverse stream is written by the same thread.
+//   forward : statements in schedule order j = 0..S-1, each  OP* TAIL
+//   reverse : statements in order j = S-1..0,          each  HEAD OP*  (ops ascending)
+__global__ void emit_level_streams_kernel(const int2* __restrict__ stmt, const double* __restrict__ mult,
+                                          const int32_t* __restrict__ idx, const uint32_t* __restrict__ sched_stmt,
+                                          const int64_t* __restrict__ foff, int64_t S, int64_t R,
+                                          Rec* __restrict__ fwd, Rec* __restrict__ rev) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t q = t; q < R; q += stride) {
+    // largest j with foff[j] <= q
+    int64_t lo = 0, hi = S - 1;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (foff[mid] <= q) lo = mid;
+      else hi = mid - 1;
+    }
+    const int64_t j = lo;
+    const uint32_t s = sched_stmt[j];
+    const int64_t o0 = stmt[s - 1].y, o1 = stmt[s].y;
+    const int64_t nrec = o1 - o0 + 1;
+    const int64_t k = q - foff[j];
+    const int64_t rbase = R - foff[j] - nrec;  // HEAD position in the reverse stream
+    Rec r;
+    if (k == nrec - 1) {
+      r.m = 0.0;
+      r.slot = stmt[s].x;
+      r.kind = REC_MARK;
+      fwd[q] = r;
+      if (rev) rev[rbase] = r;
+    } else {
+      r.m = mult[o0 + k];
+      r.slot = idx[o0 + k];
+      r.kind = REC_OP;
+      fwd[q] = r;
+      if (rev) rev[rbase + 1 + k] = r;
+    }
+  }
+}
+
+// schedule look-ups: sched_lhs[j] = LHS slot of the j-th scheduled statement;
+// pos_in_sched[s] = j.
+__global__ void sched_lookup_kernel(const int2* __restrict__ stmt, const uint32_t* __restrict__ sched_stmt, int64_t S,
+                                    int32_t* __restrict__ sched_lhs, int32_t* __restrict__ pos_in_sched) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride) {
+    const uint32_t s = sched_stmt[j];
+    sched_lhs[j] = stmt[s].x;
+    pos_in_sched[s] = static_cast<int32_t>(j);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Reverse "target stream".  In a reverse sweep every operation (m, slot X) of statement s
+// contributes m*a_s to g[X].  Inside one step several statements may name the same X, so the
+// step is replayed as a GATHER per target slot: contributions to X are listed in the
+// reference's order (statement descending, operand ascending) behind a HEAD(X) record:
+//     HEAD(X)  OP(m, k)*      k = rank of the contributing statement inside its step
+// a_s is read from the snapshot buffer abuf[k] that the step's first kernel fills.
+// Built with two stable radix sorts of the operations: by slot, then by step.
+// ---------------------------------------------------------------------------------------
+// operations in reference reverse order: rank(o) = O - end[s] + (o - end[s-1])
+__global__ void target_keys_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ idx,
+                                   int64_t n_ops, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = t; o < n_ops; o += stride) {
+    const int64_t s = stmt_of_op(stmt, n_stmt, o);
+    const int64_t rank = n_ops - stmt[s].y + (o - stmt[s - 1].y);
+    key[rank] = static_cast<uint32_t>(idx[o]);
+    val[rank] = static_cast<uint32_t>(o);
+  }
+}
+// second sort key: the step of the operation's statement
+__global__ void target_step_keys_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const uint32_t* __restrict__ val,
+                                        int64_t n_ops, const int32_t* __restrict__ level, uint32_t* __restrict__ key) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n_ops; i += stride)
+    key[i] = static_cast<uint32_t>(level[stmt_of_op(stmt, n_stmt, val[i])]);
+}
+// group boundaries: a new (step, slot) pair
+__global__ void target_flags_kernel(const uint32_t* __restrict__ step_key, const uint32_t* __restrict__ val,
+                                    const int32_t* __restrict__ idx, int64_t n_ops, int32_t* __restrict__ flag) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n_ops; i += stride) {
+    int f = 0;
+    if (i == 0 || step_key[i] != step_key[i - 1] || idx[val[i]] != idx[val[i - 1]]) f = 1;
+    flag[i] = f;
+  }
+}
+// emit the stream; incl[i] = inclusive scan of flag.  goff[g] = record offset of group g's HEAD,
+// gstep[g] = its step.
+__global__ void target_emit_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const double* __restrict__ mult,
+                                   const int32_t* __restrict__ idx, const uint32_t* __restrict__ step_key,
+                                   const uint32_t* __restrict__ val, const int32_t* __restrict__ flag,
+                                   const int32_t* __restrict__ incl, int64_t n_ops,
+                                   const int32_t* __restrict__ pos_in_sched, const int64_t* __restrict__ level_first,
+                                   Rec* __restrict__ tgt, int64_t* __restrict__ goff, int32_t* __restrict__ gstep) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n_ops; i += stride) {
+    const int64_t o = val[i];
+    const int64_t s = stmt_of_op(stmt, n_stmt, o);
+    const int64_t pos = i + incl[i];
+    Rec r;
+    r.m = mult[o];
+    r.slot = static_cast<int32_t>(pos_in_sched[s] - level_first[step_key[i]]);
+    r.kind = REC_OP;
+    tgt[pos] = r;
+    if (flag[i]) {
+      Rec h;
+      h.m = 0.0;
+      h.slot = idx[o];
+      h.kind = REC_MARK;
+      tgt[pos - 1] = h;
+      goff[incl[i] - 1] = pos - 1;
+      gstep[incl[i] - 1] = static_cast<int32_t>(step_key[i]);
+    }
+  }
+}
+// chunking of the target stream: group g opens a chunk if it is the first of its step or its
+// HEAD crosses a chunk_recs boundary.  step_group[step] = first group of the step (steps
+// without operations keep -1 and are patched on the host).
+__global__ void target_chunk_flags_kernel(const int64_t* __restrict__ goff, const int32_t* __restrict__ gstep,
+                                          int64_t n_groups, int64_t chunk_recs, int32_t* __restrict__ cflag,
+                                          int64_t* __restrict__ step_group) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g = t; g < n_groups; g += stride) {
+    int f = 0;
+    if (g == 0 || gstep[g] != gstep[g - 1]) {
+      f = 1;
+      step_group[gstep[g]] = g;
+    } else if (goff[g] / chunk_recs != goff[g - 1] / chunk_recs) {
+      f = 1;
+    }
+    cflag[g] = f;
+  }
+}
+// tchunk[c] = goff[g] for the c-th flagged group; group_chunk[g] = chunk id of group g
+__global__ void target_chunk_table_kernel(const int64_t* __restrict__ goff, const int32_t* __restrict__ cflag,
+                                          const int32_t* __restrict__ cincl, int64_t n_groups, int64_t n_tchunks,
+                                          int64_t R_t, int64_t* __restrict__ tchunk) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g = t; g < n_groups; g += stride)
+    if (cflag[g]) tchunk[cincl[g] - 1] = goff[g];
+  if (t == 0) tchunk[n_tchunks] = R_t;
+}
+
+// step tables of the target stream, on the device: patch steps without operations (they own
+// no group) to the next step's first group, then translate to chunk ids.  One thread: n_steps
+// is small.
+__global__ void target_step_tables_kernel(int64_t* __restrict__ step_group, int32_t n_steps, int64_t n_groups,
+                                          const int32_t* __restrict__ cincl, int64_t n_tchunks,
+                                          int64_t* __restrict__ step_tchunk) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  step_group[n_steps + 1] = n_groups;
+  for (int32_t l = n_steps; l >= 1; --l)
+    if (step_group[l] < 0) step_group[l] = step_group[l + 1];
+  step_group[0] = 0;
+  for (int32_t l = 1; l <= n_steps + 1; ++l) {
+    const int64_t g = step_group[l];
+    step_tchunk[l] = (g < n_groups) ? (cincl[g] - 1) : n_tchunks;
+  }
+  step_tchunk[0] = 0;
+}
+
+}  // namespace adept_b200

@@ -1,0 +1,156 @@
+/* adept_cuda.h -- C-ABI of libadept_cuda: B200-native replay of an Adept-2 derivative tape.
+ *
+ * This library replaces the REPLAY half of adept::Stack -- the bodies of
+ *   Stack::compute_adjoint          (reference adept/Stack.cpp:139-164)
+ *   Stack::compute_tangent_linear   (reference adept/Stack.cpp:170-190)
+ *   Stack::jacobian_forward[_openmp](reference adept/jacobian.cpp:127-315)
+ *   Stack::jacobian_reverse[_openmp](reference adept/jacobian.cpp:331-647)
+ * -- with hand-written sm_100a kernels.  Recording stays on the host, unchanged.
+ * The reference has no FFI of its own: the seam is the set of out-of-line Stack
+ * members above; the C++ shim that forwards them to these entry points is
+ * adept-2_b200/dropin/stack_replay_cuda.cpp.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or
+ * an ADEPT_CUDA_ERR_* code and never throws; adept_cuda_last_error() gives the text.
+ * All entry points are synchronous (results are complete on return), like the
+ * reference's.  A context may be used by one host thread at a time; use one
+ * context per adept::Stack / per host thread (reference threading model:
+ * include/adept/Stack.h:52-61).  There is NO CPU fallback: without a usable
+ * CUDA device adept_cuda_create fails.
+ */
+#ifndef ADEPT_CUDA_H
+#define ADEPT_CUDA_H 1
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct adept_cuda_ctx adept_cuda_ctx;
+
+/* status codes */
+#define ADEPT_CUDA_OK                   0
+#define ADEPT_CUDA_ERR_ARG              1   /* bad argument                                         */
+#define ADEPT_CUDA_ERR_CUDA             2   /* CUDA runtime failure (text in last_error)            */
+#define ADEPT_CUDA_ERR_NCCL             3   /* NCCL failure                                         */
+#define ADEPT_CUDA_ERR_NO_TAPE          4   /* replay requested before adept_cuda_upload_tape       */
+#define ADEPT_CUDA_ERR_RANGE            5   /* slot index outside [0,max_gradient) (reference:
+                                               gradient_out_of_range, include/adept/Stack.h:296-298)*/
+#define ADEPT_CUDA_ERR_LIMIT            6   /* tape exceeds an engine limit (documented in DESIGN.md)*/
+#define ADEPT_CUDA_ERR_NOT_IDENTIFIED  10   /* reference: dependents_or_independents_not_identified
+                                               (adept/jacobian.cpp:208-210, :466-468)               */
+#define ADEPT_CUDA_ERR_GRAD_NOT_INIT   11   /* reference: gradients_not_initialized
+                                               (adept/Stack.cpp:161-163, :187-189)                  */
+
+/* Jacobian sweep direction */
+#define ADEPT_CUDA_FORWARD 0   /* Stack::jacobian_forward: one direction per independent */
+#define ADEPT_CUDA_REVERSE 1   /* Stack::jacobian_reverse: one direction per dependent   */
+
+/* adept_cuda_adjoint / adept_cuda_tangent_linear flags */
+#define ADEPT_CUDA_SWEEP_ORDERED  1  /* bit0: strictly tape-ordered kernel (bit-exact, slow for long tapes) */
+/* default (flags==0): level-scheduled kernel built from the device-side dependency analysis. */
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+
+/* Create a context on the given CUDA devices of THIS process (n_devices >= 1; devices==NULL
+   means device 0..n_devices-1).  With n_devices > 1 the Jacobian directions are partitioned
+   over the devices: the tape is ncclBroadcast from devices[0] and result blocks are gathered
+   back on devices[0] (one process, ncclCommInitAll). */
+int  adept_cuda_create(adept_cuda_ctx** ctx, const int* devices, int n_devices);
+void adept_cuda_destroy(adept_cuda_ctx* ctx);
+
+/* One-process-per-GPU deployments (torchrun): rank 0 calls adept_cuda_unique_id, ships the
+   128 opaque bytes to every rank by any means, then every rank calls adept_cuda_join on a
+   context created with ONE device.  After that upload_tape on rank 0 + adept_cuda_share_tape
+   on all ranks broadcast the tape; adept_cuda_jacobian* is then collective: every rank
+   computes its contiguous block of directions and rank 0 receives the whole matrix. */
+int  adept_cuda_unique_id(void* id128);
+int  adept_cuda_join(adept_cuda_ctx* ctx, const void* id128, int rank, int world_size);
+int  adept_cuda_share_tape(adept_cuda_ctx* ctx, int root_rank);
+
+/* ---- the tape ------------------------------------------------------------------------ */
+
+/* Upload one recording.  `statements` is the reference's internal::Statement array
+   (include/adept/Statement.h:24-30: {int32 index; int32 end_plus_one}) of n_stmt entries
+   INCLUDING the {-1,0} sentinel pushed by new_recording (include/adept/Stack.h:528-543);
+   `multiplier`/`index` are the operation stack (include/adept/StackStorageOrig.h:155-158),
+   n_ops entries; max_gradient is Stack::max_gradient_.  The arrays are only read during the
+   call (staged through pinned memory, cudaMemcpyAsync); pinned caller memory is DMA'd
+   directly.  `epoch` is an opaque caller tag (e.g. a recording counter) returned by
+   adept_cuda_tape_epoch so a shim can tell whether its host tape changed.
+   Also builds the device-side replay streams and the level schedule. */
+int  adept_cuda_upload_tape(adept_cuda_ctx* ctx, const void* statements, int64_t n_stmt,
+                            const double* multiplier, const int32_t* index, int64_t n_ops,
+                            int64_t max_gradient, uint64_t epoch);
+int  adept_cuda_tape_epoch(const adept_cuda_ctx* ctx, uint64_t* epoch, int64_t* n_stmt, int64_t* n_ops);
+
+/* ---- replay -------------------------------------------------------------------------- */
+
+/* Jacobian of the uploaded tape.  indep/dep are Stack::independent_index_/dependent_index_
+   (include/adept/Stack.h:788-789).  Output element (i = dependent, j = independent) is
+   written to jac_out[i*dep_offset + j*indep_offset]; an offset <= 0 means "size of the other
+   dimension" exactly as adept/jacobian.cpp:215-220.  Bit-identical to the reference built
+   without FMA contraction.  jac_out is HOST memory in adept_cuda_jacobian and DEVICE memory
+   (on devices[0]) in adept_cuda_jacobian_device. */
+int  adept_cuda_jacobian(adept_cuda_ctx* ctx, int mode,
+                         const int32_t* indep, int64_t n_indep,
+                         const int32_t* dep, int64_t n_dep,
+                         double* jac_out_host, int64_t dep_offset, int64_t indep_offset);
+int  adept_cuda_jacobian_device(adept_cuda_ctx* ctx, int mode,
+                                const int32_t* indep, int64_t n_indep,
+                                const int32_t* dep, int64_t n_dep,
+                                double* jac_out_device, int64_t dep_offset, int64_t indep_offset);
+
+/* Single-direction sweeps on the caller's gradient vector (Stack::gradient_, max_gradient
+   doubles, in/out).  initialized==0 reproduces the reference's pre-check and returns
+   ADEPT_CUDA_ERR_GRAD_NOT_INIT without touching anything. */
+int  adept_cuda_tangent_linear(adept_cuda_ctx* ctx, double* gradient_host, int initialized, int flags);
+int  adept_cuda_adjoint(adept_cuda_ctx* ctx, double* gradient_host, int initialized, int flags);
+
+/* Ensemble of B tapes sharing ONE structure (statements, index, indep, dep) with per-member
+   multipliers laid out [op][member] (BASELINE config 3: simulate_radiances ensemble).  Output is
+   member-major: jac_out[b*n_dep*n_indep + i + j*n_dep] (the reference's default column-major
+   layout per member).  No counterpart in the Stack API (one Stack holds one tape). */
+int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
+                               const void* statements, int64_t n_stmt,
+                               const int32_t* index, int64_t n_ops, int64_t max_gradient,
+                               const double* multipliers, int64_t n_members,
+                               const int32_t* indep, int64_t n_indep,
+                               const int32_t* dep, int64_t n_dep,
+                               double* jac_out_host);
+
+/* ---- knobs and introspection ------------------------------------------------------- */
+
+/* Options (key, value):
+     "schedule"      0 = auto (default), 1 = always the tape-ordered kernel, 2 = always level-scheduled
+     "ref_block"     P of the reference build being matched (1,2,4,8,16,32; default 2): granularity of
+                     the reverse-mode "skip the statement if all P lanes are zero" test
+                     (adept/jacobian.cpp:392-407).  Only visible with non-finite multipliers.
+     "pass_dirs"     max directions resident per pass (0 = as many as fit in workspace_bytes)
+     "workspace_bytes" cap for the direction-major gradient workspace (0 = 60% of free memory)
+     "warps_per_cta" replay CTA size in warps (1..8, default 8)
+     "window"        statements per dependency-analysis window (0 = default 65536)
+     "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
+                     (stats "dominant_ms", "dominant_launches"); off by default
+*/
+int  adept_cuda_set_option(adept_cuda_ctx* ctx, const char* key, int64_t value);
+
+/* Statistics of the last call (key -> value): "n_levels", "n_chunks", "n_records",
+   "kernel_launches" (cumulative count of this library's own kernel launches),
+   "replay_ms" (CUDA-event time of the last replay: zero-fill+seed+sweep+extract(+gather)),
+   "sweep_ms" (the replay kernels alone), "upload_ms", "analysis_ms", "d2h_ms",
+   "used_schedule" (1 ordered / 2 level), "pass_dirs", "n_passes". */
+int  adept_cuda_get_stat(const adept_cuda_ctx* ctx, const char* key, double* value);
+
+/* Copies the per-statement level (1-based; level[0]=0 for the sentinel) of the last
+   uploaded tape to the host: the device-side dependency analysis, exposed for tests. */
+int  adept_cuda_get_levels(adept_cuda_ctx* ctx, int32_t* level_out, int64_t n_stmt);
+
+const char* adept_cuda_last_error(const adept_cuda_ctx* ctx);
+const char* adept_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADEPT_CUDA_H */

@@ -155,44 +155,54 @@ int oracle_jacobian_reverse(const int32_t* stmt, int64_t n_stmt, const double* m
 
 /* Sequential reference for the dependency analysis the CUDA engine does on the
    device (no counterpart in the reference: it replays strictly in tape order).
-   level[s] (1-based, level[0] = 0 for the sentinel) is the earliest step at
-   which statement s may run if statements are only reordered in ways that
-   cannot change any bit of the result:
-     mode 0 (gather sweeps, forward): RAW, WAR and WAW on slots are kept;
-                                      concurrent readers of a slot are allowed.
-     mode 1 (scatter sweeps, reverse): every pair of statements touching a common
-                                      slot keeps its tape order (so that the
-                                      accumulation order into each slot is the
-                                      reference's: statement descending, operand
-                                      ascending).
-   Returns the number of levels. */
+   level[s] (1-based; level[0] = 0 for the sentinel) is the earliest step at which
+   statement s may run under a constraint set that keeps every bit of every sweep:
+     mode 0: RAW, WAR and WAW on slots; concurrent readers of a slot version are free.
+             Enough for gather sweeps (forward), where each statement sums its own
+             operands in tape order.
+     mode 1: every pair of statements touching a common slot keeps its tape order.
+     mode 2: mode 0 plus "readers of one slot version have non-decreasing levels in tape
+             order".  A reverse sweep that walks levels downwards and, inside a level,
+             adds the contributions to each slot in (statement descending, operand
+             ascending) order then reproduces the reference's accumulation order exactly.
+   `window` > 0 restarts the analysis every `window` statements (levels are then local
+   to the window; the schedule is (window, level) lexicographic).  Returns the number of
+   steps (sum of the windows' depths). */
 int64_t oracle_levels(const int32_t* stmt, int64_t n_stmt, const int32_t* idx,
-                      int64_t max_gradient, int mode, int32_t* level) {
+                      int64_t max_gradient, int mode, int64_t window, int32_t* level) {
   int32_t* wl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* level of last writer  */
-  int32_t* rl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* max level of readers since */
+  int32_t* rl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* max level of readers of the current version */
+  int64_t* ep = (int64_t*)calloc((size_t)max_gradient, sizeof(int64_t)); /* window tag of the entry */
+  int64_t steps = 0;
   int32_t depth = 0;
+  int64_t cur_win = 1;
   level[0] = 0;
   for (int64_t s = 1; s < n_stmt; ++s) {
+    if (window > 0 && (s - 1) % window == 0 && s > 1) { steps += depth; depth = 0; ++cur_win; }
+#define TOUCH(x) do { if (ep[x] != cur_win) { ep[x] = cur_win; wl[x] = 0; rl[x] = 0; } } while (0)
     int32_t lv = 0;
     int32_t L = LHS(s);
+    TOUCH(L);
     for (int64_t op = END(s-1); op < END(s); ++op) {
       int32_t x = idx[op];
-      if (wl[x] > lv) lv = wl[x];
-      if (mode == 1 && rl[x] > lv) lv = rl[x];
+      TOUCH(x);
+      if (wl[x] + 1 > lv) lv = wl[x] + 1;
+      if (mode == 1 && rl[x] + 1 > lv) lv = rl[x] + 1;
+      if (mode == 2 && rl[x] > lv) lv = rl[x];
     }
-    if (wl[L] > lv) lv = wl[L];
-    if (rl[L] > lv) lv = rl[L];
-    lv += 1;
+    if (wl[L] + 1 > lv) lv = wl[L] + 1;
+    if (rl[L] + 1 > lv) lv = rl[L] + 1;
+    if (lv < 1) lv = 1;
     level[s] = lv;
     for (int64_t op = END(s-1); op < END(s); ++op) {
       int32_t x = idx[op];
       if (lv > rl[x]) rl[x] = lv;
     }
+    /* the write retires the old version (a statement's own reads belong to it) */
     wl[L] = lv; rl[L] = (mode == 1) ? lv : 0;
-    /* a statement that reads its own LHS: in mode 0 the read belongs to the old
-       version, which this write retires, so rl is reset above. */
     if (lv > depth) depth = lv;
   }
-  free(wl); free(rl);
-  return depth;
+  steps += depth;
+  free(wl); free(rl); free(ep);
+  return steps;
 }

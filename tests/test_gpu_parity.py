@@ -1,0 +1,268 @@
+"""GPU (-m gpu): parity of the CUDA path, through the C-ABI, against the oracle.
+
+Bar (BASELINE.json north_star): Jacobians and sweeps are BIT-IDENTICAL in double to the reference
+built without FMA contraction -- for the tape-ordered kernels AND for the level-scheduled ones
+(this engine's level schedule keeps every accumulation order, so no tolerance is needed; the
+1e-10 the north star would allow for a reordered adjoint is not used).  NaNs compare as a class.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, same_bits
+
+pytestmark = pytest.mark.gpu
+
+ORDERED, LEVELS = 1, 2
+
+
+def upload(engine, t, schedule, window=0):
+    engine.set_option("schedule", schedule)
+    engine.set_option("window", window)
+    engine.set_option("pass_dirs", 0)
+    engine.set_option("ref_block", 2)
+    engine.upload_tape(t["stmt"], t["mult"], t["idx"], t["max_gradient"])
+
+
+def check_jacobians(engine, po, t, what=""):
+    for mode in (0, 1):
+        got = engine.jacobian(mode, t["indep"], t["dep"])
+        rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], mode,
+                               n_threads=0)
+        assert rc == 0
+        assert same_bits(got, want), f"{what} mode {mode}: {int(np.sum(got != want))} of {got.size} elements differ"
+
+
+# ---- golden vectors (made by the real reference) --------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("schedule,window", [(ORDERED, 0), (LEVELS, 0), (LEVELS, 64), (LEVELS, 1000)])
+def test_golden_jacobians(engine, name, schedule, window):
+    g = load_golden(name)
+    upload(engine, g, schedule, window)
+    assert same_bits(engine.jacobian(0, g["indep"], g["dep"]), g["jac_fwd"]), "forward"
+    assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"]), "reverse"
+    assert engine.stat("used_schedule") == schedule
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("schedule,window", [(ORDERED, 0), (LEVELS, 0), (LEVELS, 100)])
+def test_golden_sweeps(engine, pkg, name, schedule, window):
+    g = load_golden(name)
+    upload(engine, g, schedule, window)
+    flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
+    assert same_bits(engine.tangent_linear(g["g_tl_in"], True, flags), g["g_tl_out"]), "tangent linear"
+    assert same_bits(engine.adjoint(g["g_ad_in"], True, flags), g["g_ad_out"]), "adjoint"
+
+
+# ---- the device-side dependency analysis ------------------------------------------------------------
+@pytest.mark.parametrize("window", [0, 64, 777, 4096])
+def test_levels_match_the_sequential_rule(engine, po, pkg, window):
+    for t in (pkg.tapegen.advection_tape("toon", 96, 40), pkg.tapegen.synthetic_tape(30000, 11, 64, seed=5),
+              pkg.tapegen.rosenbrock_tape(3000)):
+        upload(engine, t, LEVELS, window)
+        got = engine.levels()
+        steps, local = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=window or 65536)
+        assert engine.stat("n_levels") == steps
+        # device levels are global step numbers: (window, local level) in lexicographic order
+        W = window or 65536
+        S = t["stmt"].shape[0] - 1
+        base = 0
+        for w0 in range(1, S + 1, W):
+            seg = slice(w0, min(S + 1, w0 + W))
+            assert np.array_equal(got[seg] - base, local[seg])
+            base += int(local[seg].max())
+
+
+# ---- adversarial little tapes: slot reuse, self reference, repeated operands, empty statements -----
+@pytest.mark.parametrize("seed", range(6))
+def test_random_tapes(engine, po, pkg, seed):
+    rng = np.random.default_rng(100 + seed)
+    t = pkg.tapegen.random_small_tape(rng, int(rng.integers(50, 6000)), int(rng.integers(8, 300)),
+                                      n_indep=int(rng.integers(1, 70)) if seed else 1,
+                                      n_dep=int(rng.integers(1, 7)))
+    for schedule, window in ((ORDERED, 0), (LEVELS, 0), (LEVELS, 97)):
+        upload(engine, t, schedule, window)
+        check_jacobians(engine, po, t, f"seed {seed} schedule {schedule} window {window}")
+        g0 = rng.uniform(-1, 1, t["max_gradient"])
+        flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
+        assert same_bits(engine.adjoint(g0, True, flags), po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
+        assert same_bits(engine.tangent_linear(g0, True, flags), po.tangent_linear(t["stmt"], t["mult"], t["idx"], g0))
+
+
+def test_empty_and_tiny_tapes(engine, po):
+    # only the sentinel: every Jacobian entry is d(slot)/d(slot)
+    t = dict(stmt=np.array([[-1, 0]], np.int32), mult=np.zeros(0), idx=np.zeros(0, np.int32), max_gradient=4,
+             indep=np.array([0, 1], np.int32), dep=np.array([1, 2], np.int32))
+    upload(engine, t, 0)
+    check_jacobians(engine, po, t, "sentinel only")
+    # one statement without operands (x = constant) and one with
+    t = dict(stmt=np.array([[-1, 0], [2, 0], [1, 1]], np.int32), mult=np.array([3.0]), idx=np.array([0], np.int32),
+             max_gradient=3, indep=np.array([0], np.int32), dep=np.array([1, 2], np.int32))
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule)
+        check_jacobians(engine, po, t, "tiny")
+
+
+# ---- output layout: dep_offset / indep_offset exactly as adept/jacobian.cpp:215-220 ---------------
+def test_offsets(engine, po, pkg):
+    rng = np.random.default_rng(7)
+    t = pkg.tapegen.random_small_tape(rng, 800, 60, n_indep=37, n_dep=5)
+    n, m = 37, 5
+    upload(engine, t, LEVELS, 50)
+    for mode in (0, 1):
+        for do, io in ((1, 0), (0, 1), (n, 1), (1, m + 2), (n + 3, 1), (2, 2 * m + 1), (0, 0)):
+            size = 1 + (m - 1) * (do if do > 0 else n) + (n - 1) * (io if io > 0 else m)
+            got = engine.jacobian(mode, t["indep"], t["dep"], out=np.full(size, np.nan), dep_offset=do, indep_offset=io)
+            rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], mode,
+                                   dep_offset=do, indep_offset=io, out=np.full(size, np.nan))
+            assert rc == 0 and same_bits(got, want), (mode, do, io)
+
+
+def test_multiple_passes(engine, po, pkg):
+    t = pkg.tapegen.advection_tape("lw", 100, 30)
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule)
+        engine.set_option("pass_dirs", 32)        # 100 directions -> 4 passes, the last one partial
+        check_jacobians(engine, po, t, f"passes schedule {schedule}")
+        assert engine.stat("n_passes") == 4
+    engine.set_option("pass_dirs", 0)
+
+
+# ---- error behaviour (reference: exceptions thrown before the sweep; here: status codes) -----------
+def test_errors(pkg):
+    eng = pkg.Engine([0])
+    with pytest.raises(pkg.cuda_replay_error):                                   # no tape yet
+        eng.jacobian(0, [0], [1])
+    t = pkg.tapegen.radiance_tape()
+    eng.upload_tape(t["stmt"], t["mult"], t["idx"], t["max_gradient"])
+    with pytest.raises(pkg.dependents_or_independents_not_identified):          # adept/jacobian.cpp:208-210
+        eng.jacobian(0, [], t["dep"])
+    with pytest.raises(pkg.dependents_or_independents_not_identified):
+        eng.jacobian(1, t["indep"], [])
+    with pytest.raises(pkg.gradients_not_initialized):                          # adept/Stack.cpp:161-163
+        eng.adjoint(np.zeros(t["max_gradient"]), initialized=False)
+    with pytest.raises(pkg.gradients_not_initialized):
+        eng.tangent_linear(np.zeros(t["max_gradient"]), initialized=False)
+    with pytest.raises(pkg.gradient_out_of_range):                              # slot outside the gradient list
+        eng.jacobian(0, [t["max_gradient"] + 5], t["dep"])
+    bad = t["idx"].copy(); bad[3] = t["max_gradient"] + 100
+    with pytest.raises(pkg.gradient_out_of_range):                              # malformed tape is refused, not replayed
+        eng.upload_tape(t["stmt"], t["mult"], bad, t["max_gradient"])
+    eng.close()
+
+
+# ---- non-finite multipliers: the only place where the reference's block width P is visible --------
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_non_finite_multipliers_follow_the_reference_block_rule(engine, po, pkg, P):
+    rng = np.random.default_rng(3)
+    t = pkg.tapegen.random_small_tape(rng, 500, 40, n_indep=6, n_dep=9)
+    t["mult"][rng.integers(0, t["mult"].size, 12)] = np.inf
+    t["mult"][rng.integers(0, t["mult"].size, 6)] = np.nan
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule, 64)
+        engine.set_option("ref_block", P)
+        for mode in (0, 1):
+            got = engine.jacobian(mode, t["indep"], t["dep"])
+            rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], mode, P=P)
+            assert rc == 0 and same_bits(got, want), (schedule, mode, P)
+    engine.set_option("ref_block", 2)
+
+
+# ---- the reference's own test workloads at full size ----------------------------------------------------
+def test_thread_safe_workload(engine, po, pkg):
+    """test/test_thread_safe.cpp:36-113: Toon NX=128, 200 steps, 128x128 Jacobian by forward AND reverse
+    sweeps; the reference's criterion is RMSD(fwd, rev) <= 1e-5; ours is bit equality with the
+    reference itself (oracle/_ref when it travelled to this box, else the pinned restatement)."""
+    if po.ref_available(""):
+        rt = po.RefTape().record_advection("toon", 128, 200)
+        t = rt.arrays()
+        want = {0: rt.jacobian(0, n_threads=0), 1: rt.jacobian(1, n_threads=0)}
+    else:
+        t = pkg.tapegen.advection_tape("toon", 128, 200)
+        want = {m: po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], m)[1]
+                for m in (0, 1)}
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule)
+        jf = engine.jacobian(0, t["indep"], t["dep"])
+        jr = engine.jacobian(1, t["indep"], t["dep"])
+        assert same_bits(jf, want[0]) and same_bits(jr, want[1])
+        assert np.sqrt(np.mean((jf - jr) ** 2)) <= 1e-5
+
+
+def test_autodiff_benchmark_workload(engine, po, pkg):
+    """BASELINE config 1: Lax-Wendroff NX=100, nt=2000, full 100x100 Jacobian (398100 / 1384100 / 299)."""
+    t = pkg.tapegen.advection_tape("lw", 100, 2000)
+    assert (t["stmt"].shape[0] - 1, t["idx"].size, t["max_gradient"]) == (398100, 1384100, 299)
+    upload(engine, t, 0)
+    check_jacobians(engine, po, t, "lw 100x2000")
+
+
+def test_rosenbrock_adjoint_with_a_long_statement(engine, po, pkg):
+    """BASELINE config 5 shape (test/test_minimizer.cpp:39-49,103-115): one statement holds 4(N-1) operands."""
+    t = pkg.tapegen.rosenbrock_tape(20000)
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule)
+        g0 = np.zeros(t["max_gradient"]); g0[t["dep"][0]] = 1.0      # cost.set_gradient(1.0)
+        flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
+        got = engine.adjoint(g0, True, flags)
+        assert same_bits(got, po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
+        x = np.zeros(t["max_gradient"]); x[t["indep"]] = np.linspace(-1, 1, t["indep"].size)
+        assert same_bits(engine.tangent_linear(x, True, flags), po.tangent_linear(t["stmt"], t["mult"], t["idx"], x))
+    check_jacobians(engine, po, t, "rosenbrock jacobian (1 x N: reverse; forward has N directions)")
+
+
+def test_synthetic_config4_shape(engine, po, pkg):
+    """BASELINE config 4 at reduced length: 2e5 statements, 2^14 slots, 256x256; parity on the full matrix."""
+    t = pkg.tapegen.synthetic_tape(200_000, 14, 256, seed=42)
+    upload(engine, t, LEVELS)
+    check_jacobians(engine, po, t, "synthetic")
+    assert engine.stat("used_schedule") == LEVELS
+
+
+# ---- size-independent properties at a size the oracle would not finish quickly ------------------------
+def test_large_toon_properties(engine, pkg):
+    """Toon NX=1024, nt=300 (1.06e6 statements): forward == reverse to rounding (the reference's own
+    criterion, test/test_thread_safe.cpp:86-113), level schedule == tape order bit for bit, and linearity:
+    J v from the tangent-linear sweep equals the Jacobian applied to v."""
+    t = pkg.tapegen.advection_tape("toon", 1024, 300)
+    upload(engine, t, LEVELS)
+    jf = engine.jacobian(0, t["indep"], t["dep"]).reshape(1024, 1024)      # [indep, dep]
+    jr = engine.jacobian(1, t["indep"], t["dep"]).reshape(1024, 1024)
+    assert np.sqrt(np.mean((jf - jr) ** 2)) <= 1e-5
+    rng = np.random.default_rng(0)
+    v = np.zeros(t["max_gradient"]); v[t["indep"]] = rng.uniform(-1, 1, 1024)
+    tl = engine.tangent_linear(v)[t["dep"]]
+    np.testing.assert_allclose(tl, v[t["indep"]] @ jf, rtol=1e-9, atol=1e-12)
+    upload(engine, t, ORDERED)
+    sub = np.arange(0, 1024, 16).astype(np.int32)                           # 64 columns through the ordered kernel
+    jo = engine.jacobian(0, t["indep"][sub], t["dep"]).reshape(64, 1024)
+    assert same_bits(jo, jf[sub])
+    jo = engine.jacobian(1, t["indep"], t["dep"][sub]).reshape(1024, 64)
+    assert same_bits(jo, jr[:, sub])
+
+
+# ---- the Stack mirror: reads like the reference's test_adept / test_thread_safe -----------------------
+def test_stack_api(pkg, po):
+    g = load_golden("algorithm")
+    s = pkg.Stack()
+    s.load_tape(g["stmt"], g["mult"], g["idx"], g["max_gradient"])
+    s.independent(g["indep"]); s.dependent(g["dep"])
+    assert same_bits(s.jacobian(), g["jac_rev"])                  # 2 independents > 1 dependent: reverse
+    assert same_bits(s.jacobian_forward(), g["jac_fwd"])
+    J = s.jacobian_matrix()
+    assert J.shape == (1, 2)
+    s.set_gradients(0, g["max_gradient"], g["g_ad_in"])
+    s.reverse()
+    assert same_bits(s.get_gradients(0, g["max_gradient"]), g["g_ad_out"])
+    s.clear_gradients()
+    s.set_gradients(0, g["max_gradient"], g["g_tl_in"])
+    s.forward()
+    assert same_bits(s.get_gradients(0, g["max_gradient"]), g["g_tl_out"])
+    # recording continues after a Jacobian call: the device copy must follow (ownership)
+    s2 = pkg.Stack()
+    x = s2.register_gradients(2); y = s2.register_gradient()
+    s2.new_recording()
+    s2.push_rhs(2.0, x); s2.push_rhs(3.0, x + 1); s2.push_lhs(y)
+    s2.independent([x, x + 1]); s2.dependent(y)
+    assert s2.jacobian().tolist() == [2.0, 3.0]
+    s2.push_rhs(10.0, y); s2.push_lhs(y)                          # y *= 10
+    assert s2.jacobian().tolist() == [20.0, 30.0]
