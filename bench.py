@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: Jacobian tape-entry x direction per second (+ % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1, one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of synthetic input: one whole Jacobian of the
+workload's tape.  Default workload (N = 1): BASELINE config 2 -- Toon advection nx=4096, 1000
+time steps (8 195 096 statements / 36 858 096 operations / 12 287 slots), 4096x4096 Jacobian by
+REVERSE sweeps on B200s.  With N > 1 the directions of the same Jacobian are
+partitioned over the ranks: tape ncclBroadcast from rank 0, result blocks gathered on rank 0
+(total work fixed => "scaling": "strong").
+
+One JSON line on rank 0:
+  value        whole-job op*dir/s with the tape and its schedule already resident in HBM when the timed
+               region starts (what the reference times around stack_.jacobian(), differentiator.h:338-348);
+               the timed region holds zero-fill + seeding + sweep + extraction (+ NCCL gather).
+  e2e          the same metric through the C-ABI call a user makes, with HOST buffers: pinned H2D of the
+               tape (+ device-side schedule construction) and D2H of the Jacobian inside the timed region.
+  roofline     dominant replay kernel: ALGORITHMIC bytes per launch / its CUDA-event launch time, against
+               the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline the reference's own OpenMP Stack::jacobian_reverse (oracle/_ref, built from the unmodified
+               reference) on this box's host cores, on a bounded sample of the same Jacobian's rows.
+--impl reference prints the reference's CPU arm as the main line instead.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Jacobian tape-entry x direction per second (batched replay of the recorded derivative tape)"
+UNIT = "op*dir/s"
+
+WORKLOADS = {
+    # name: (description, tape builder, mode)
+    "toon4096": dict(desc="BASELINE config 2: Toon advection nx=4096 nt=1000 (8195096 stmts / 36858096 ops / 12287 slots), "
+                          "4096x4096 Jacobian, reverse sweeps", scheme="toon", nx=4096, nt=1000, mode=1),
+    "toon1024": dict(desc="reduced config 2: Toon advection nx=1024 nt=250, 1024x1024 Jacobian, reverse sweeps",
+                     scheme="toon", nx=1024, nt=250, mode=1),
+    "lw100": dict(desc="BASELINE config 1: Lax-Wendroff nx=100 nt=2000, 100x100 Jacobian, forward sweeps",
+                  scheme="lw", nx=100, nt=2000, mode=0),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_tape(w):
+    pkg = importlib.import_module("adept-2_b200")
+    return pkg.tapegen.advection_tape(w["scheme"], w["nx"], w["nt"])
+
+
+def alg_bytes_per_opdir(S, O, mode):
+    """forward 8(1+S/O), reverse 16(1+S/O) bytes of gradient traffic per op*dir."""
+    return (8.0 if mode == 0 else 16.0) * (1.0 + S / O)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------
+def reference_rate(tape, mode, target_seconds=12.0, variant=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po   # checker / CPU baseline only
+
+    variant = po.best_ref_variant() if variant is None else variant
+    kind = "reference"
+    O = tape["idx"].size
+    if po.ref_available(variant):
+        rt = po.RefTape(variant)
+        P = rt.packet_size
+        threads = po._ref(variant).ref_max_threads()
+        rt.inject(tape["stmt"], tape["mult"], tape["idx"], tape["max_gradient"] - 1, tape["indep"], tape["dep"])
+
+        def run(dirs):
+            if mode == 0:
+                rt.set_io(tape["indep"][:dirs], tape["dep"])
+            else:
+                rt.set_io(tape["indep"], tape["dep"][:dirs])
+            rt.jacobian(mode, n_threads=0)
+            return rt.last_seconds
+    else:   # the restatement, if the compiled reference did not travel
+        kind = "port"
+        P, threads = 8, os.cpu_count() or 1
+
+        def run(dirs):
+            ind = tape["indep"][:dirs] if mode == 0 else tape["indep"]
+            dep = tape["dep"] if mode == 0 else tape["dep"][:dirs]
+            t0 = time.perf_counter()
+            po.jacobian(tape["stmt"], tape["mult"], tape["idx"], tape["max_gradient"], ind, dep, mode, P=P, n_threads=0)
+            return time.perf_counter() - t0
+    D_all = tape["indep"].size if mode == 0 else tape["dep"].size
+    d = min(D_all, threads * P)              # calibration: one block per thread
+    t = run(d)
+    dirs = int(min(D_all, max(threads * P, (target_seconds / max(t, 1e-6)) * d // (threads * P) * threads * P)))
+    return dict(run=run, dirs=dirs, P=P, threads=threads, kind=kind, variant=variant or "sse2", O=O)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="toon4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--schedule", type=int, default=0)
+    ap.add_argument("--pass-dirs", type=int, default=0)
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=8)
+    args = ap.parse_args()
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    mode = wl["mode"]
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        tape = build_tape(wl)
+        S, O = tape["stmt"].shape[0] - 1, tape["idx"].size
+        r = reference_rate(tape, mode, target_seconds=8.0)
+        for _ in range(W):
+            r["run"](min(r["dirs"], r["threads"] * r["P"]))
+        ts = [r["run"](r["dirs"]) for _ in range(K)]
+        t = sum(ts) / K
+        value = O * r["dirs"] / t
+        sample = (f"{r['dirs']} of {tape['dep'].size if mode else tape['indep'].size} directions "
+                  f"({'rows' if mode else 'columns'}) of the same Jacobian per step; rate is linear in blocks "
+                  f"(adept/jacobian.cpp:146-147); build {r['variant']} P={r['P']} -O3 -ffp-contract=off")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "statements": S, "operations": O},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module("adept-2_b200")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = pkg.Engine([local_rank])
+    if world > 1:
+        ids = [eng.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.join(ids[0], rank, world)
+    eng.set_option("schedule", args.schedule)
+    eng.set_option("pass_dirs", args.pass_dirs)
+    eng.set_option("window", args.window)
+    eng.set_option("warps_per_cta", args.warps)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tape = build_tape(wl) if rank == 0 else None
+    meta = [None]
+    if rank == 0:
+        meta = [dict(S=int(tape["stmt"].shape[0] - 1), O=int(tape["idx"].size), G=int(tape["max_gradient"]),
+                     indep=tape["indep"], dep=tape["dep"])]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    m = meta[0]
+    S, O, G = m["S"], m["O"], m["G"]
+    indep, dep = m["indep"], m["dep"]
+    N, M = indep.size, dep.size
+    D = N if mode == 0 else M
+    work = float(O) * D
+
+    # pinned host copies of the tape (what a Stack shim would hand over) and of the result
+    if rank == 0:
+        pin = {k: torch.from_numpy(np.ascontiguousarray(tape[k])).pin_memory() for k in ("stmt", "mult", "idx")}
+        host = {k: v.numpy() for k, v in pin.items()}
+        out_pin = torch.empty(N * M, dtype=torch.float64).pin_memory()
+    h2d = (S + 1) * 8 + O * 12 + (N + M) * 4
+    d2h = N * M * 8
+
+    def upload():
+        if rank == 0:
+            eng.upload_tape(host["stmt"], host["mult"], host["idx"], G)
+        if world > 1:
+            eng.share_tape(0)
+
+    upload()
+    out_dev = torch.empty(N * M, dtype=torch.float64, device="cuda") if rank == 0 else None
+    out_ptr = out_dev.data_ptr() if rank == 0 else 0
+
+    def step():
+        eng.jacobian_device(mode, indep, dep, out_ptr)   # collective when world > 1
+        return eng.stat("replay_ms", 0.0)
+
+    for _ in range(W):
+        step()
+    launches0 = eng.stat("kernel_launches", 0.0)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    ev_ms = 0.0
+    for _ in range(K):
+        ev_ms += step()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stat("kernel_launches", 0.0) - launches0
+    wall = torch.tensor([t1 - t0, ev_ms / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    wall_s, ev_s = float(wall[0]), float(wall[1])
+    value = work * K / wall_s
+
+    # dominant kernel, every launch bracketed by CUDA events on its own stream (one extra step)
+    eng.set_option("time_kernels", 1)
+    step()
+    dom_ms, dom_launches = eng.stat("dominant_ms", 0.0), eng.stat("dominant_launches", 0.0)
+    sweep_ms = eng.stat("sweep_ms", 0.0)
+    used = eng.stat("used_schedule", 0.0)
+    eng.set_option("time_kernels", 0)
+
+    # end to end through the C-ABI with host buffers: H2D of the tape + schedule build + replay + D2H
+    barrier()
+    e2e_s = None
+    phases = {}
+    if args.e2e_steps > 0:
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            upload()
+            if rank == 0:
+                eng.jacobian(mode, indep, dep, out=out_pin.numpy())
+            else:
+                eng.jacobian_device(mode, indep, dep, 0)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        for k in ("upload_ms", "analysis_ms", "bcast_ms", "replay_ms", "d2h_ms"):
+            phases[k] = eng.stat(k, None)
+        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_t[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # parity spot check inside the bench (checker only): a few rows against the oracle, bit for bit
+    parity = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle as po
+        sub = np.linspace(0, D - 1, 8).astype(np.int32)
+        ind = indep[sub] if mode == 0 else indep
+        dp = dep if mode == 0 else dep[sub]
+        rc, want = po.jacobian(tape["stmt"], tape["mult"], tape["idx"], G, ind, dp, mode, n_threads=0)
+        if not args.e2e_steps:   # nothing was copied to the host yet
+            out_pin.copy_(out_dev)
+            torch.cuda.synchronize()
+        full = out_pin.numpy().reshape(N, M)
+        got = full[sub, :] if mode == 0 else full[:, sub]
+        parity = bool(rc == 0 and np.array_equal(np.ascontiguousarray(got).ravel().view(np.uint64), want.view(np.uint64)))
+    except Exception as e:  # the bench number does not depend on the checker being present
+        parity = f"not checked: {e}"
+
+    peak, peak_src = peaks()
+    bpo = alg_bytes_per_opdir(S, O, mode)
+    # algorithmic bytes of the dominant kernel: the per-operation part (reverse: 16 B, forward: 8 B per op*dir;
+    # the per-statement part belongs to the snapshot kernel / the TAIL stores)
+    dom_bytes = (16.0 if mode else 8.0) * work / world if used == 2 and mode == 1 else bpo * work / world
+    roof = None
+    if dom_ms and dom_launches:
+        ach = dom_bytes / (dom_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "reverse_target_kernel" if (mode == 1 and used == 2) else
+                ("replay_reverse_kernel" if mode == 1 else "replay_forward_kernel"),
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": dom_launches,
+                "algorithmic_bytes_per_launch": dom_bytes / dom_launches,
+                "avg_launch_us": 1e3 * dom_ms / dom_launches,
+                "whole_sweep_frac": (bpo * work / world) / (sweep_ms / 1e3) / 1e9 / peak if sweep_ms else None,
+                "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
+                        "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = reference_rate(tape, mode, target_seconds=12.0)
+            t = r["run"](r["dirs"])
+            cpu = {"value": O * r["dirs"] / t, "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
+                   "sample": f"{r['dirs']} of {D} directions of the same Jacobian, {t:.1f} s, build {r['variant']} "
+                             f"P={r['P']}, OpenMP Stack::jacobian_{'reverse' if mode else 'forward'}"}
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * wall_s / K, "ms_per_step_cuda_events": 1e3 * ev_s / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "statements": S, "operations": O, "slots": G, "directions": D,
+                   "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}",
+                   "schedule": {1.0: "tape-ordered", 2.0: "level"}.get(used, "?"),
+                   "steps_in_schedule": eng.stat("n_levels", 0), "pass_dirs": eng.stat("pass_dirs", 0),
+                   "n_passes": eng.stat("n_passes", 0),
+                   "l2": "inputs larger than L2: tape streams %.0f MB + workspace %.0f MB per step" %
+                         (16e-6 * (O + S), 8e-6 * G * min(D, eng.stat("pass_dirs", D) or D))},
+        "clocks": clocks,
+        "e2e": {"value": (work / e2e_s) if e2e_s else None, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s if e2e_s else None, "phases_ms": phases},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "parity_bit_exact_vs_oracle": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

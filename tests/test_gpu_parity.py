@@ -219,25 +219,34 @@ def test_synthetic_config4_shape(engine, po, pkg):
 
 
 # ---- size-independent properties at a size the oracle would not finish quickly ------------------------
-def test_large_toon_properties(engine, pkg):
-    """Toon NX=1024, nt=300 (1.06e6 statements): forward == reverse to rounding (the reference's own
-    criterion, test/test_thread_safe.cpp:86-113), level schedule == tape order bit for bit, and linearity:
-    J v from the tangent-linear sweep equals the Jacobian applied to v."""
+def test_large_advection_properties(engine, pkg):
+    """NX=1024, nt=300 (1.06e6 statements), too big for a quick oracle run: size-independent properties.
+    Toon: forward == reverse to rounding (the reference's own criterion, test/test_thread_safe.cpp:86-113)
+    and level schedule == tape order, bit for bit.  Lax-Wendroff (a stable scheme: the Toon recurrence
+    amplifies rounding differences between two summation paths): linearity, J v from one tangent-linear
+    sweep equals the forward Jacobian applied to v, and v^T J from one adjoint sweep likewise."""
     t = pkg.tapegen.advection_tape("toon", 1024, 300)
     upload(engine, t, LEVELS)
     jf = engine.jacobian(0, t["indep"], t["dep"]).reshape(1024, 1024)      # [indep, dep]
     jr = engine.jacobian(1, t["indep"], t["dep"]).reshape(1024, 1024)
     assert np.sqrt(np.mean((jf - jr) ** 2)) <= 1e-5
-    rng = np.random.default_rng(0)
-    v = np.zeros(t["max_gradient"]); v[t["indep"]] = rng.uniform(-1, 1, 1024)
-    tl = engine.tangent_linear(v)[t["dep"]]
-    np.testing.assert_allclose(tl, v[t["indep"]] @ jf, rtol=1e-9, atol=1e-12)
     upload(engine, t, ORDERED)
     sub = np.arange(0, 1024, 16).astype(np.int32)                           # 64 columns through the ordered kernel
     jo = engine.jacobian(0, t["indep"][sub], t["dep"]).reshape(64, 1024)
     assert same_bits(jo, jf[sub])
     jo = engine.jacobian(1, t["indep"], t["dep"][sub]).reshape(1024, 64)
     assert same_bits(jo, jr[:, sub])
+
+    t = pkg.tapegen.advection_tape("lw", 1024, 300)
+    upload(engine, t, LEVELS)
+    jf = engine.jacobian(0, t["indep"], t["dep"]).reshape(1024, 1024)
+    jr = engine.jacobian(1, t["indep"], t["dep"]).reshape(1024, 1024)
+    np.testing.assert_allclose(jf, jr, rtol=0, atol=1e-13)
+    rng = np.random.default_rng(0)
+    v = np.zeros(t["max_gradient"]); v[t["indep"]] = rng.uniform(-1, 1, 1024)
+    np.testing.assert_allclose(engine.tangent_linear(v)[t["dep"]], v[t["indep"]] @ jf, rtol=0, atol=1e-12)
+    u = np.zeros(t["max_gradient"]); u[t["dep"]] = rng.uniform(-1, 1, 1024)
+    np.testing.assert_allclose(engine.adjoint(u)[t["indep"]], jr @ u[t["dep"]], rtol=0, atol=1e-12)
 
 
 # ---- the Stack mirror: reads like the reference's test_adept / test_thread_safe -----------------------
