@@ -29,7 +29,7 @@ using namespace adept_b200;
 
 namespace {
 
-constexpr int64_t kChunkRecs = 512;          // target records per level chunk
+constexpr int64_t kChunkRecs = 128;          // target records per level chunk (one CTA's share of a step)
 constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
@@ -76,7 +76,7 @@ struct Shard {
   std::vector<int64_t> step_tchunk;   // [n_levels+2] first target chunk of each step
   std::vector<LongStmt> long_stmts;
   // workspace
-  Buf g, abuf, seed_slots, out_slots, out, g1, a1, scratch;
+  Buf g, abuf, rowact, aflag, seed_slots, out_slots, out, g1, a1, scratch;
   // optional per-launch timing of the dominant replay kernel (option "time_kernels")
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
@@ -295,6 +295,13 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
                  &lchunk, &pos_in_sched, &incl, &gstep, &cflag, &cincl, &sgroup, &stchunk, &lo, &lc})
     tmps.add(*b);
 
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char* key) {
+    cudaStreamSynchronize(s.stream);
+    auto now = std::chrono::steady_clock::now();
+    s.stat[key] = std::chrono::duration<double, std::milli>(now - tp).count();
+    tp = now;
+  };
   // 3. dependency analysis: one warp per window of statements (tape_kernels.cuh)
   const int64_t W = c->opt_window > 0 ? c->opt_window : kDefaultWindow;
   const int64_t n_windows = (S + W - 1) / W;
@@ -329,6 +336,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   s.n_levels = n_levels;
   if (n_levels < 1) return fail(errp, ADEPT_CUDA_ERR_CUDA, "dependency analysis produced no steps");
 
+  lap("an_window_ms");
   // 4. statements sorted by step (stable), record offsets, chunk table, level-major forward stream
   const int64_t nmax = std::max(S, O);
   RET(ensure(errp, k0, size_t(nmax) * 4));
@@ -386,6 +394,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   for (int32_t l = 1; l <= n_levels; ++l)
     s.max_step_width = std::max(s.max_step_width, s.level_first[l + 1] - s.level_first[l]);
 
+  lap("an_forward_ms");
   // 5. reverse target stream: operations sorted by (step, slot, reference reverse order)
   s.step_group.assign(size_t(n_levels) + 2, 0);
   s.step_tchunk.assign(size_t(n_levels) + 2, 0);
@@ -445,6 +454,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     CK(cudaStreamSynchronize(s.stream));
   }
 
+  lap("an_target_ms");
   // 6. long statements (rare): listed for the single-direction forward sweep
   {
     const int max_long = 4096;
@@ -569,17 +579,19 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     B.chunk_begin = s.tchunk.as<int64_t>();
     B.g = g;
     B.abuf = s.abuf.as<double>();
+    B.rowact = s.rowact.as<uint8_t>();
+    B.aflag = s.aflag.as<uint8_t>();
     B.K = K;
     B.n_colblocks = A.n_colblocks;
+    B.flag_pitch = int(K / 32);
     B.n_dirs = n_dirs;
     B.ref_block = c->opt_ref_block;
-    const int snap_warps = 8;
     for (int32_t l = s.n_levels; l >= 1; --l) {
       const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
       if (n <= 0) continue;
-      reverse_snapshot_kernel<<<dim3(unsigned((n + snap_warps - 1) / snap_warps), unsigned(A.n_colblocks)),
-                                snap_warps * 32, 0, s.stream>>>(s.sched_lhs.as<int32_t>(), j0, n, g,
-                                                                 s.abuf.as<double>(), K, n_dirs);
+      reverse_snapshot_kernel<<<unsigned((n * A.n_colblocks + 255) / 256), 256, 0, s.stream>>>(
+          s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
+          s.aflag.as<uint8_t>(), int(K / 32), A.n_colblocks);
       s.launches += 1;
       const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
       if (c1 > c0) {
@@ -626,12 +638,20 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     double* g = s.g.as<double>();
     int n_passes = 0;
     const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
-    if (plan.use_levels && mode == 1) RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
+    const int ncb_pass = int(K / 32);
+    const bool sparse = plan.use_levels && mode == 1;
+    if (sparse) {
+      RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
+      RET(ensure(errp, s.rowact, size_t(s.max_gradient) * size_t(ncb_pass)));
+      RET(ensure(errp, s.aflag, size_t(std::max<int64_t>(s.max_step_width, 1)) * size_t(ncb_pass)));
+    }
     for (int64_t d0 = d_lo; d0 < d_hi; d0 += pass) {
       const int64_t n = std::min(pass, d_hi - d0);
       const bool last = d0 + pass >= d_hi;
       CK(cudaMemsetAsync(g, 0, size_t(s.max_gradient) * size_t(K) * 8, s.stream));
-      seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n));
+      if (sparse) CK(cudaMemsetAsync(s.rowact.p, 0, size_t(s.max_gradient) * size_t(ncb_pass), s.stream));
+      seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n),
+                                                                    sparse ? s.rowact.as<uint8_t>() : nullptr, ncb_pass);
       s.launches += 1;
       if (last) CK(cudaEventRecord(s.ev[2], s.stream));
       RET(launch_sweep(c, s, mode, g, K, n, plan));
@@ -977,7 +997,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.abuf, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -1131,7 +1151,9 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   c->stat["n_records"] = double(s.R);
   c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
   c->stat["kernel_launches"] = c->total_launches();
+  for (const char* k : {"an_window_ms", "an_forward_ms", "an_target_ms"}) c->stat[k] = s.stat[k];
   c->epoch = epoch;
+  c->stat["upload_total_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return 0;
 }
 

@@ -29,7 +29,7 @@
 namespace adept_b200 {
 
 constexpr int kBatch = 8;          // gradient loads in flight per warp
-constexpr int kPieceRecs = 256;    // records per TMA stage (4 KB)
+constexpr int kPieceRecs = 256;    // records per TMA stage (4 KB); level chunks (~128 records) fit one stage
 constexpr int kStages = 4;         // ring depth
 
 struct ReplayArgs {
@@ -64,7 +64,7 @@ __device__ __forceinline__ void issue_piece(StageRing& ring, const Rec* chunk, i
 // chunks, where no OP reads a slot that any TAIL of the same level writes.
 // ---------------------------------------------------------------------------------------
 template <bool CHECK>
-__global__ void __launch_bounds__(256) replay_forward_kernel(ReplayArgs A) {
+__global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {
   __shared__ StageRing ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -226,16 +226,58 @@ __global__ void __launch_bounds__(256) replay_reverse_kernel(ReplayArgs A) {
 // A contribution is dropped when the contributing statement's a is zero in every lane of the
 // reference's P-lane block (adept/jacobian.cpp:392-407), as in the scatter kernel above.
 // ---------------------------------------------------------------------------------------
+// Structural sparsity.  A Jacobian row/column usually touches a small part of the tape (the
+// reference exploits this in reverse mode by skipping statements whose adjoint block is zero,
+// adept/jacobian.cpp:392-407).  Here the unit is (slot row, 32-lane column block):
+//   rowact[slot*ncb + cb] == 0  =>  g[slot][32*cb .. 32*cb+31] is all +0.0
+//   aflag[k*ncb + cb]     == 0  =>  the snapshot a_s of statement k is all zero in that block
+// A zero block contributes exactly nothing in the reference either (the whole block is zero, so
+// every P-lane sub-block is skipped), so eliding its loads, arithmetic and stores keeps all bits.
+// One thread looks at one (statement, column block) pair; the active pairs of the CTA are
+// compacted in shared memory and moved one 256-byte row per warp.
 __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __restrict__ sched_lhs, int64_t j0,
                                                                int64_t n_stmts, double* __restrict__ g,
-                                                               double* __restrict__ abuf, int64_t K, int64_t n_dirs) {
+                                                               double* __restrict__ abuf, int64_t K, int64_t n_dirs,
+                                                               uint8_t* __restrict__ rowact,
+                                                               uint8_t* __restrict__ aflag, int pitch, int ncb_live) {
+  __shared__ int list[256];
+  __shared__ int cnt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t k = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
-  const int64_t d = static_cast<int64_t>(blockIdx.y) * 32 + lane;
-  if (k >= n_stmts || d >= n_dirs) return;
-  double* p = g + static_cast<int64_t>(sched_lhs[j0 + k]) * K + d;
-  abuf[k * K + d] = *p;
-  *p = 0.0;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
+  const int64_t total = n_stmts * ncb_live;
+  {
+    const int64_t t = t0 + threadIdx.x;
+    if (t < total) {
+      const int64_t k = t / ncb_live;
+      const int cb = static_cast<int>(t - k * ncb_live);
+      const int64_t lhs = sched_lhs[j0 + k];
+      if (rowact[lhs * pitch + cb]) list[atomicAdd(&cnt, 1)] = threadIdx.x;
+      else aflag[k * pitch + cb] = 0;  // the row is all zero: a_s = 0, nothing to move
+    }
+  }
+  __syncthreads();
+  const int n = cnt;
+  for (int q = warp; q < n; q += (blockDim.x >> 5)) {
+    const int64_t t = t0 + list[q];
+    const int64_t k = t / ncb_live;
+    const int cb = static_cast<int>(t - k * ncb_live);
+    const int64_t lhs = sched_lhs[j0 + k];
+    const int64_t d = static_cast<int64_t>(cb) * 32 + lane;
+    const bool ok = d < n_dirs;
+    double* p = g + lhs * K + d;
+    const double a = ok ? *p : 0.0;
+    const bool any = __ballot_sync(0xffffffffu, a != 0.0) != 0u;
+    if (any && ok) {
+      abuf[k * K + d] = a;
+      *p = 0.0;
+    }
+    if (lane == 0) {
+      aflag[k * pitch + cb] = any ? 1 : 0;
+      rowact[lhs * pitch + cb] = 0;  // zeroed (or found zero)
+    }
+  }
 }
 
 struct TargetArgs {
@@ -244,14 +286,21 @@ struct TargetArgs {
   int64_t first_chunk;
   double* g;
   const double* abuf;
+  uint8_t* rowact;
+  const uint8_t* aflag;
   int64_t K;
-  int n_colblocks;
+  int n_colblocks;   // live column blocks of this pass
+  int flag_pitch;    // row pitch of rowact/aflag (K/32)
   int64_t n_dirs;
   int ref_block;
 };
 
-__global__ void __launch_bounds__(256) reverse_target_kernel(TargetArgs A) {
+// The CTA first fetches, in one round trip and for all its warps, the activity byte of every
+// record of the staged piece (pf); a warp whose column block has no active contribution in the
+// piece skips it outright, so dead (target, column block) pairs cost no gradient traffic.
+__global__ void __launch_bounds__(256, 4) reverse_target_kernel(TargetArgs A) {
   __shared__ StageRing ring;
+  __shared__ uint8_t pf[kPieceRecs][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int64_t c = A.first_chunk + blockIdx.x;
@@ -259,11 +308,14 @@ __global__ void __launch_bounds__(256) reverse_target_kernel(TargetArgs A) {
   const int64_t n_recs = r1 - r0;
   const Rec* chunk = A.recs + r0;
   const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
-  const int cb = blockIdx.y * nwarps + warp;
+  const int cb0 = blockIdx.y * nwarps;
+  const int cb = cb0 + warp;
+  const int ncb = A.flag_pitch;
   const bool live = cb < A.n_colblocks;
   const bool lane_ok = static_cast<int64_t>(cb) * 32 + lane < A.n_dirs;
   double* gcol = A.g + static_cast<int64_t>(cb) * 32 + lane;
   const double* acol = A.abuf + static_cast<int64_t>(cb) * 32 + lane;
+  uint8_t* ract = A.rowact + cb;
   const uint32_t P = static_cast<uint32_t>(A.ref_block);
   const uint32_t grp_mask = (P >= 32 ? 0xffffffffu : ((1u << P) - 1u)) << ((lane / P) * P);
 
@@ -276,41 +328,86 @@ __global__ void __launch_bounds__(256) reverse_target_kernel(TargetArgs A) {
     for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
 
   double acc = 0.0;
-  int32_t cur = -1;  // slot whose sum is in acc
+  int32_t cur = -1;        // slot whose sum is (or will be) in acc
+  bool acc_valid = false;  // acc holds g[cur] (+ contributions)
+  bool dirty = false;      // acc differs from what memory holds
   for (int64_t p = 0; p < n_pieces; ++p) {
     const int st = static_cast<int>(p % kStages);
     mbar_wait(&ring.full[st], static_cast<uint32_t>((p / kStages) & 1));
     const int64_t left = n_recs - p * kPieceRecs;
     const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
     const Rec* r = &ring.buf[st][0];
+    // 1. activity bytes of the piece: thread t -> record t / nwarps, column block cb0 + t % nwarps
+    for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
+      const int i = t / nwarps, w = t - i * nwarps;
+      const int32_t slot = r[i].slot;
+      uint8_t f = 0;
+      if (cb0 + w < A.n_colblocks && slot >= 0)
+        f = (r[i].kind == REC_MARK) ? A.rowact[static_cast<int64_t>(slot) * ncb + cb0 + w]
+                                    : A.aflag[static_cast<int64_t>(slot) * ncb + cb0 + w];
+      pf[i][w] = f;
+    }
+    __syncthreads();
     if (live) {
-      for (int i = 0; i < n; i += kBatch) {
-        Rec rc[kBatch];
-        double v[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          if (i + u < n) rc[u] = r[i + u];
-          else { rc[u].m = 0.0; rc[u].slot = -1; rc[u].kind = REC_OP; }
+      // does any contribution of this piece reach my column block?
+      bool mine = false;
+      for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[i][warp] != 0);
+      if (!__any_sync(0xffffffffu, mine)) {
+        // nothing to add: retire the open target; remember the last HEAD for a group that goes on
+        if (dirty) {
+          if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+          if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+          dirty = false;
         }
-        // all loads of a step are independent of its stores: targets are distinct, abuf is read-only
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          v[u] = 0.0;
-          if (lane_ok && rc[u].slot >= 0)
-            v[u] = (rc[u].kind == REC_MARK) ? gcol[static_cast<int64_t>(rc[u].slot) * A.K]
-                                            : acol[static_cast<int64_t>(rc[u].slot) * A.K];
+        int last = -1;
+        for (int i = lane; i < n; i += 32)
+          if (r[i].kind == REC_MARK) last = i;
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (last >= 0) {
+          cur = r[last].slot;
+          acc_valid = false;
         }
+      } else {
+        for (int i = 0; i < n; i += kBatch) {
+          Rec rc[kBatch];
+          double v[kBatch];
+          uint8_t f[kBatch];
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          if (rc[u].slot < 0) continue;
-          if (rc[u].kind == REC_MARK) {  // next target: retire the previous one
-            if (cur >= 0 && lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
-            cur = rc[u].slot;
-            acc = v[u];
-          } else {
-            const double a = v[u];
-            const uint32_t nz = __ballot_sync(0xffffffffu, a != 0.0);
-            if ((nz & grp_mask) != 0u) acc = mul_add_rn(acc, rc[u].m, a);
+          for (int u = 0; u < kBatch; ++u) {
+            if (i + u < n) { rc[u] = r[i + u]; f[u] = pf[i + u][warp]; }
+            else { rc[u].m = 0.0; rc[u].slot = -1; rc[u].kind = REC_OP; f[u] = 0; }
+          }
+          // data of the active records only; all loads of a step are independent of its stores
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            v[u] = 0.0;
+            if (f[u] && lane_ok)
+              v[u] = (rc[u].kind == REC_MARK) ? gcol[static_cast<int64_t>(rc[u].slot) * A.K]
+                                              : acol[static_cast<int64_t>(rc[u].slot) * A.K];
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (rc[u].slot < 0) continue;
+            if (rc[u].kind == REC_MARK) {  // next target: retire the previous one
+              if (dirty) {
+                if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+                if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+              }
+              cur = rc[u].slot;
+              acc = v[u];  // +0.0 when the row is inactive
+              acc_valid = true;
+              dirty = false;
+            } else if (f[u]) {
+              if (!acc_valid) {  // the group began in a piece this warp skipped
+                acc = 0.0;
+                if (ract[static_cast<int64_t>(cur) * ncb] && lane_ok) acc = gcol[static_cast<int64_t>(cur) * A.K];
+                acc_valid = true;
+              }
+              const double a = v[u];
+              const uint32_t nz = __ballot_sync(0xffffffffu, a != 0.0);
+              if ((nz & grp_mask) != 0u) acc = mul_add_rn(acc, rc[u].m, a);
+              dirty = true;
+            }
           }
         }
       }
@@ -318,16 +415,24 @@ __global__ void __launch_bounds__(256) reverse_target_kernel(TargetArgs A) {
     __syncthreads();
     if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
   }
-  if (live && cur >= 0 && lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+  if (live && dirty) {
+    if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+    if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
 // Seeding and extraction (adept/jacobian.cpp:163-190 forward, :372-379 and :434-449 reverse).
 // ---------------------------------------------------------------------------------------
 // g[seed_slot[d0+j]*K + j] = 1.0 for the n directions of this pass.
-__global__ void seed_kernel(double* g, int64_t K, const int32_t* seed_slot, int64_t d0, int n) {
+__global__ void seed_kernel(double* g, int64_t K, const int32_t* seed_slot, int64_t d0, int n, uint8_t* rowact,
+                            int ncb) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) g[static_cast<int64_t>(seed_slot[d0 + j]) * K + j] = 1.0;
+  if (j < n) {
+    const int64_t slot = seed_slot[d0 + j];
+    g[slot * K + j] = 1.0;
+    if (rowact) rowact[slot * ncb + (j >> 5)] = 1;  // several lanes may store the same 1
+  }
 }
 
 // out[i*stride_i + (d0+j)*stride_j] = g[out_slot[i]*K + j], i < n_out, j < n_dirs.

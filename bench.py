@@ -303,15 +303,23 @@ def main():
     phases = {}
     if args.e2e_steps > 0:
         t0 = time.perf_counter()
+        t_up = t_jac = 0.0
         for _ in range(args.e2e_steps):
+            ta = time.perf_counter()
             upload()
+            tb = time.perf_counter()
             if rank == 0:
                 eng.jacobian(mode, indep, dep, out=out_pin.numpy())
             else:
                 eng.jacobian_device(mode, indep, dep, 0)
+            t_up += tb - ta
+            t_jac += time.perf_counter() - tb
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        for k in ("upload_ms", "analysis_ms", "bcast_ms", "replay_ms", "d2h_ms"):
+        phases["upload_call_ms"] = 1e3 * t_up / args.e2e_steps
+        phases["jacobian_call_ms"] = 1e3 * t_jac / args.e2e_steps
+        for k in ("upload_ms", "analysis_ms", "an_window_ms", "an_forward_ms", "an_target_ms", "bcast_ms", "replay_ms",
+                  "d2h_ms", "jacobian_wall_ms", "upload_total_ms"):
             phases[k] = eng.stat(k, None)
         e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
