@@ -34,6 +34,7 @@ constexpr int64_t kLongThreshold = 1024;     // records; longer statements get c
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
 constexpr size_t kStageBytes = size_t(32) << 20;
+constexpr size_t kPoolKeepBytes = size_t(8) << 30;  // analysis temporaries kept between uploads up to this size
 
 struct Buf {
   void* p = nullptr;
@@ -80,6 +81,7 @@ struct Shard {
   // optional per-launch timing of the dominant replay kernel (option "time_kernels")
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
+  std::vector<Buf> pool;  // analysis temporaries (build_schedule)
   // per-shard bookkeeping (shards may be driven by worker threads)
   std::string err;
   double launches = 0;
@@ -209,12 +211,6 @@ int upload(Shard& s, void* dst, const void* src, size_t bytes) {
 // ---------------------------------------------------------------------------------------
 // Schedule construction on one shard (tape already on the device).
 // ---------------------------------------------------------------------------------------
-struct BufSet {  // temporaries freed on every exit path
-  std::vector<Buf*> all;
-  Buf& add(Buf& b) { all.push_back(&b); return b; }
-  ~BufSet() { for (Buf* b : all) release(*b); }
-};
-
 int sort_pairs(std::string* errp, Shard& s, Buf& k0, Buf& k1, Buf& v0, Buf& v1, Buf& tmp, int64_t n, int nbits) {
   cub::DoubleBuffer<uint32_t> dk(k0.as<uint32_t>(), k1.as<uint32_t>());
   cub::DoubleBuffer<uint32_t> dv(v0.as<uint32_t>(), v1.as<uint32_t>());
@@ -288,12 +284,24 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   const bool want_levels = (c->opt_schedule != 1) && (S >= kMinLevelStatements || c->opt_schedule == 2);
   if (!want_levels) return 0;
 
-  BufSet tmps;
-  Buf cap, tab_off, tables, wdepth, wbase, k0, k1, v0, v1, tmp, nrec, lfirst, flag, cid, lchunk, pos_in_sched, incl,
-      gstep, cflag, cincl, sgroup, stchunk, lo, lc;
-  for (Buf* b : {&cap, &tab_off, &tables, &wdepth, &wbase, &k0, &k1, &v0, &v1, &tmp, &nrec, &lfirst, &flag, &cid,
-                 &lchunk, &pos_in_sched, &incl, &gstep, &cflag, &cincl, &sgroup, &stchunk, &lo, &lc})
-    tmps.add(*b);
+  // Temporaries live in a per-shard pool that survives the call (re-uploads of similar tapes then cost
+  // no cudaMalloc/cudaFree, which dominated and jittered the analysis time); a pool above
+  // kPoolKeepBytes is released on exit.
+  struct PoolGuard {
+    Shard& s;
+    ~PoolGuard() {
+      size_t total = 0;
+      for (Buf& b : s.pool) total += b.bytes;
+      if (total > kPoolKeepBytes)
+        for (Buf& b : s.pool) release(b);
+    }
+  } pool_guard{s};
+  s.pool.resize(24);
+  Buf &cap = s.pool[0], &tab_off = s.pool[1], &tables = s.pool[2], &wdepth = s.pool[3], &wbase = s.pool[4],
+      &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &nrec = s.pool[10],
+      &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &pos_in_sched = s.pool[15],
+      &incl = s.pool[16], &gstep = s.pool[17], &cflag = s.pool[18], &cincl = s.pool[19], &sgroup = s.pool[20],
+      &stchunk = s.pool[21], &lo = s.pool[22], &lc = s.pool[23];
 
   auto tp = std::chrono::steady_clock::now();
   auto lap = [&](const char* key) {
@@ -332,7 +340,6 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   s.launches += 1;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaGetLastError());
-  release(tables);
   s.n_levels = n_levels;
   if (n_levels < 1) return fail(errp, ADEPT_CUDA_ERR_CUDA, "dependency analysis produced no steps");
 
@@ -1006,6 +1013,7 @@ void free_shard(Shard& s) {
   for (int k = 0; k < 4; ++k)
     if (s.ev[k]) cudaEventDestroy(s.ev[k]);
   for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
+  for (Buf& b : s.pool) release(b);
   if (s.comm) ncclCommDestroy(s.comm);
   if (s.stream) cudaStreamDestroy(s.stream);
 }

@@ -298,7 +298,8 @@ struct TargetArgs {
 // The CTA first fetches, in one round trip and for all its warps, the activity byte of every
 // record of the staged piece (pf); a warp whose column block has no active contribution in the
 // piece skips it outright, so dead (target, column block) pairs cost no gradient traffic.
-__global__ void __launch_bounds__(256, 4) reverse_target_kernel(TargetArgs A) {
+// (3 CTAs of 8 warps per SM: at 4 the register cap forces spills into the inner loop, measured 20% slower)
+__global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
   __shared__ StageRing ring;
   __shared__ uint8_t pf[kPieceRecs][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -106,9 +106,9 @@ __global__ void build_streams_kernel(const int2* __restrict__ stmt, int64_t n_st
 // ---------------------------------------------------------------------------------------
 struct __align__(16) SlotEntry {
   int32_t key;  // slot, -1 = empty   (tables are memset to 0xFF: key = wl = rl = -1)
-  int32_t wl;   // step of the last writer   (<= 0: none in this window)
-  int32_t rl;   // max step of the readers of the current version (<= 0: none)
   int32_t pad;
+  int32_t wl;   // step of the last writer   (<= 0: none in this window)          } 8-byte aligned pair,
+  int32_t rl;   // max step of the readers of the current version (<= 0: none)    } written together
 };
 
 // capacity (power of two >= 2 * touches) of every window's table
@@ -130,12 +130,25 @@ __device__ __forceinline__ uint32_t slot_hash(int32_t x) {
   uint32_t h = static_cast<uint32_t>(x) * 0x9E3779B1u;
   return h ^ (h >> 15);
 }
-// find the entry of slot x, inserting it if absent
-__device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, int32_t x) {
+// Find (or insert) the entry of slot x and return its (writer step, reader step).  One 16-byte
+// L2 read in the common case; the CAS is only needed for a slot's first touch in the window.
+__device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, int32_t x, int32_t& wl, int32_t& rl) {
   uint32_t h = slot_hash(x) & mask;
   while (true) {
-    const int32_t k = atomicCAS(&T[h].key, -1, x);
-    if (k == -1 || k == x) return &T[h];
+    const int4 e = __ldcg(reinterpret_cast<const int4*>(&T[h]));
+    if (e.x == x) {
+      wl = e.z;
+      rl = e.w;
+      return &T[h];
+    }
+    if (e.x == -1) {
+      const int32_t k = atomicCAS(&T[h].key, -1, x);
+      if (k == -1 || k == x) {  // fresh (possibly inserted by a sibling lane just now): no writer, no reader
+        wl = -1;
+        rl = -1;
+        return &T[h];
+      }
+    }
     h = (h + 1) & mask;
   }
 }
@@ -155,33 +168,59 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   const uint32_t mask = static_cast<uint32_t>(tab_off[w + 1] - tab_off[w]) - 1u;
   int32_t depth = 0;
   int64_t o0 = stmt[lo - 1].y;
+  int2 st = stmt[lo];
   for (int64_t s = lo; s <= hi; ++s) {
-    const int2 st = stmt[s];
     const int64_t o1 = st.y;
+    const int32_t lhs = st.x;
+    const int64_t nops = o1 - o0;
+    const int2 st_next = (s < hi) ? stmt[s + 1] : st;  // prefetch: independent of the table work below
     int32_t lv = 1;
-    for (int64_t o = o0 + lane; o < o1; o += 32) {
-      SlotEntry* e = table_entry(T, mask, idx[o]);
-      const int32_t wl = __ldcg(&e->wl), rl = __ldcg(&e->rl);
-      lv = max(lv, max(wl + 1, rl));       // RAW (strict), MONO (non-strict); empty = -1 -> 0, -1
-    }
-    SlotEntry* eL = table_entry(T, mask, st.x);
-    lv = max(lv, max(__ldcg(&eL->wl), __ldcg(&eL->rl)) + 1);  // WAW, WAR (strict)
+    if (nops < 32) {
+      // one pass: lane < nops handles an operand, lane == nops the LHS
+      const int32_t x = (lane < nops) ? idx[o0 + lane] : (lane == nops ? lhs : -1);
+      SlotEntry* e = nullptr;
+      if (x >= 0) {
+        int32_t wl, rl;
+        e = table_entry(T, mask, x, wl, rl);
+        lv = (lane < nops) ? max(wl + 1, rl)          // RAW (strict), MONO (non-strict); empty = -1
+                           : max(wl, rl) + 1;         // WAW, WAR (strict)
+        lv = max(lv, 1);
+      }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-    __syncwarp();
-    for (int64_t o = o0 + lane; o < o1; o += 32) {
-      SlotEntry* e = table_entry(T, mask, idx[o]);
-      __stcg(&e->rl, lv);                   // lv >= the old rl by MONO
-    }
-    __syncwarp();
-    if (lane == 0) {                        // the write retires the old version and its readers
-      __stcg(&eL->wl, lv);
-      __stcg(&eL->rl, 0);
-      level[s] = lv;
+      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+      if (lane < nops) __stcg(&e->rl, lv);            // lv >= the old rl by MONO
+      __syncwarp();
+      if (lane == nops) {                             // the write retires the old version and its readers
+        __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(lv, 0));
+        level[s] = lv;
+      }
+    } else {
+      for (int64_t o = o0 + lane; o < o1; o += 32) {
+        int32_t wl, rl;
+        table_entry(T, mask, idx[o], wl, rl);
+        lv = max(lv, max(wl + 1, rl));
+      }
+      int32_t wl, rl;
+      SlotEntry* eL = table_entry(T, mask, lhs, wl, rl);
+      lv = max(lv, max(wl, rl) + 1);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+      __syncwarp();
+      for (int64_t o = o0 + lane; o < o1; o += 32) {
+        int32_t a, b;
+        SlotEntry* e = table_entry(T, mask, idx[o], a, b);
+        __stcg(&e->rl, lv);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __stcg(reinterpret_cast<int2*>(&eL->wl), make_int2(lv, 0));
+        level[s] = lv;
+      }
     }
     __syncwarp();
     depth = max(depth, lv);
     o0 = o1;
+    st = st_next;
   }
   if (lane == 0) win_depth[w] = depth;
 }

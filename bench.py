@@ -51,6 +51,12 @@ WORKLOADS = {
                      scheme="toon", nx=1024, nt=250, mode=1),
     "lw100": dict(desc="BASELINE config 1: Lax-Wendroff nx=100 nt=2000, 100x100 Jacobian, forward sweeps",
                   scheme="lw", nx=100, nt=2000, mode=0),
+    "synthetic1e7_fwd": dict(desc="BASELINE config 4 at 1/10 length: seeded random tape, 1e7 statements (mean 4 operands), "
+                                  "2^20 slots, 8192x8192 Jacobian, forward sweeps", scheme="synthetic", n=10_000_000,
+                             log2_slots=20, n_io=8192, mode=0),
+    "synthetic1e7_rev": dict(desc="BASELINE config 4 at 1/10 length: seeded random tape, 1e7 statements (mean 4 operands), "
+                                  "2^20 slots, 8192x8192 Jacobian, reverse sweeps", scheme="synthetic", n=10_000_000,
+                             log2_slots=20, n_io=8192, mode=1),
 }
 
 
@@ -113,6 +119,8 @@ class ClockSampler:
 
 def build_tape(w):
     pkg = importlib.import_module("adept-2_b200")
+    if w["scheme"] == "synthetic":
+        return pkg.tapegen.synthetic_tape(w["n"], w["log2_slots"], w["n_io"], seed=42)
     return pkg.tapegen.advection_tape(w["scheme"], w["nx"], w["nt"])
 
 
