@@ -550,7 +550,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
                  const SweepPlan& plan) {
   std::string* errp = &s.err;
   if (s.R == 0) return 0;
-  ReplayArgs A;
+  ReplayArgs A{};
   A.g = g;
   A.K = K;
   A.n_colblocks = int((n_dirs + 31) / 32);
@@ -563,8 +563,8 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     A.chunk_begin = s.one_chunk.as<int64_t>();
     A.first_chunk = 0;
     if (c->opt_time_kernels) RET(mark(s));
-    if (mode == 0) replay_forward_kernel<true><<<dim3(1, gy), threads, 0, s.stream>>>(A);
-    else replay_reverse_kernel<<<dim3(1, gy), threads, 0, s.stream>>>(A);
+    if (mode == 0) replay_forward_kernel<true, false><<<dim3(1, gy), threads, 0, s.stream>>>(A);
+    else replay_reverse_kernel<false><<<dim3(1, gy), threads, 0, s.stream>>>(A);
     if (c->opt_time_kernels) RET(mark(s));
     s.launches += 1;
   } else if (mode == 0) {
@@ -575,7 +575,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       if (c1 <= c0) continue;
       A.first_chunk = c0;
       if (c->opt_time_kernels) RET(mark(s));
-      replay_forward_kernel<false><<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(A);
+      replay_forward_kernel<false, false><<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(A);
       if (c->opt_time_kernels) RET(mark(s));
       s.launches += 1;
     }
@@ -925,7 +925,7 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
   const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
   if (s.R > 0) {
     if (ordered) {
-      ReplayArgs A;
+      ReplayArgs A{};
       A.g = g;
       A.K = 1;
       A.n_colblocks = 1;
@@ -934,8 +934,8 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
       A.recs = (adjoint ? s.rev_t : s.fwd_t).as<Rec>();
       A.chunk_begin = s.one_chunk.as<int64_t>();
       A.first_chunk = 0;
-      if (adjoint) replay_reverse_kernel<<<dim3(1, 1), 32, 0, s.stream>>>(A);
-      else replay_forward_kernel<true><<<dim3(1, 1), 32, 0, s.stream>>>(A);
+      if (adjoint) replay_reverse_kernel<false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
+      else replay_forward_kernel<true, false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
       s.launches += 1;
     } else {
       const Rec* recs = s.fwd_l.as<Rec>();
@@ -1240,11 +1240,126 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
                               const int32_t* index, int64_t n_ops, int64_t max_gradient, const double* multipliers,
                               int64_t n_members, const int32_t* indep, int64_t n_indep, const int32_t* dep,
                               int64_t n_dep, double* jac_out_host) {
-  (void)mode; (void)statements; (void)n_stmt; (void)index; (void)n_ops; (void)max_gradient; (void)multipliers;
-  (void)n_members; (void)indep; (void)n_indep; (void)dep; (void)n_dep; (void)jac_out_host;
   if (!c) return ADEPT_CUDA_ERR_ARG;
   std::string* errp = &c->err;
-  return fail(errp, ADEPT_CUDA_ERR_ARG, "adept_cuda_jacobian_batch: not built yet");
+  if (mode != ADEPT_CUDA_FORWARD && mode != ADEPT_CUDA_REVERSE) return fail(errp, ADEPT_CUDA_ERR_ARG, "mode must be 0 or 1");
+  if (n_indep <= 0 || n_dep <= 0)
+    return fail(errp, ADEPT_CUDA_ERR_NOT_IDENTIFIED, "dependent or independent variables not identified");
+  if (!statements || n_stmt < 1 || n_ops < 0 || max_gradient < 1 || n_members < 1 || !indep || !dep || !jac_out_host ||
+      (n_ops > 0 && (!index || !multipliers)))
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "bad ensemble arguments");
+  for (int64_t i = 0; i < n_indep; ++i)
+    if (indep[i] < 0 || indep[i] >= max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "independent slot out of range");
+  for (int64_t i = 0; i < n_dep; ++i)
+    if (dep[i] < 0 || dep[i] >= max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "dependent slot out of range");
+  const int64_t D = (mode == 0) ? n_indep : n_dep;
+  const int64_t n_out = (mode == 0) ? n_dep : n_indep;
+  const int32_t* seeds = (mode == 0) ? indep : dep;
+  const int32_t* outs = (mode == 0) ? dep : indep;
+  const int P = c->opt_ref_block;
+  const int Dp = int(((D + P - 1) / P) * P);  // the reference's P-lane blocks stay inside one member
+  const int n_sh = int(c->sh.size());
+  const int64_t per = (n_members + n_sh - 1) / n_sh;
+  auto t_begin = std::chrono::steady_clock::now();
+  RET(over_shards(c, [&](size_t k) -> int {
+    Shard& s = c->sh[k];
+    std::string* errp = &s.err;
+    const int64_t b_lo = std::min<int64_t>(n_members, int64_t(k) * per), b_hi = std::min<int64_t>(n_members, b_lo + per);
+    if (b_hi <= b_lo) return 0;
+    CK(cudaSetDevice(s.dev));
+    // the shared structure replaces whatever tape this context held
+    s.have_tape = false;
+    s.have_levels = false;
+    RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
+    RET(ensure(errp, s.idx, size_t(n_ops) * 4));
+    RET(upload(s, s.stmt.p, statements, size_t(n_stmt) * 8));
+    RET(upload(s, s.idx.p, index, size_t(n_ops) * 4));
+    s.n_stmt = n_stmt;
+    s.n_ops = n_ops;
+    s.max_gradient = max_gradient;
+    const int64_t S = n_stmt - 1, R = n_ops + S;
+    s.R = R;
+    RET(ensure(errp, s.scratch, 64));
+    CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
+    validate_kernel<<<grid_for(std::max(n_ops, n_stmt), 256, s.sm_count), 256, 0, s.stream>>>(
+        s.stmt.as<int2>(), n_stmt, s.idx.as<int32_t>(), n_ops, max_gradient, s.scratch.as<int>());
+    s.launches += 1;
+    int flags = 0;
+    CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (flags) return fail(errp, ADEPT_CUDA_ERR_RANGE, "malformed tape structure");
+    const int64_t one_chunk_host[2] = {0, R};
+    RET(ensure(errp, s.one_chunk, sizeof one_chunk_host));
+    CK(cudaMemcpyAsync(s.one_chunk.p, one_chunk_host, sizeof one_chunk_host, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    RET(ensure(errp, s.fwd_t, size_t(std::max<int64_t>(R, 1)) * sizeof(Rec)));
+    RET(ensure(errp, s.rev_t, size_t(std::max<int64_t>(R, 1)) * sizeof(Rec)));
+    if (R > 0) {
+      build_streams_kernel<<<grid_for(std::max(n_ops, S), 256, s.sm_count), 256, 0, s.stream>>>(
+          s.stmt.as<int2>(), n_stmt, nullptr, s.idx.as<int32_t>(), n_ops, s.fwd_t.as<Rec>(), s.rev_t.as<Rec>(), nullptr);
+      s.launches += 1;
+    }
+    RET(ensure(errp, s.seed_slots, size_t(D) * 4));
+    RET(ensure(errp, s.out_slots, size_t(n_out) * 4));
+    CK(cudaMemcpyAsync(s.seed_slots.p, seeds, size_t(D) * 4, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.out_slots.p, outs, size_t(n_out) * 4, cudaMemcpyHostToDevice, s.stream));
+    // members per pass from the workspace budget: per member max_gradient*Dp gradients + n_ops multipliers + outputs
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes)
+                                                     : size_t(double(free_b + s.g.bytes + s.mult.bytes + s.out.bytes) * 0.6);
+    const size_t per_member = size_t(max_gradient) * Dp * 8 + size_t(n_ops) * 8 + size_t(n_dep) * n_indep * 8;
+    int64_t nb_pass = std::max<int64_t>(1, int64_t(budget / per_member));
+    nb_pass = std::min<int64_t>(nb_pass, b_hi - b_lo);
+    nb_pass = std::min<int64_t>(nb_pass, (int64_t(65535) * 8 * 32) / Dp);  // gridDim.y limit
+    for (int64_t b0 = b_lo; b0 < b_hi; b0 += nb_pass) {
+      const int64_t nb = std::min(nb_pass, b_hi - b0);
+      const int64_t lanes = nb * Dp;
+      const int64_t K = ((lanes + 31) / 32) * 32;
+      RET(ensure(errp, s.g, size_t(max_gradient) * size_t(K) * 8));
+      RET(ensure(errp, s.mult, size_t(std::max<int64_t>(n_ops, 1)) * size_t(nb) * 8));
+      RET(ensure(errp, s.out, size_t(nb) * n_dep * n_indep * 8));
+      if (n_ops > 0)
+        CK(cudaMemcpy2DAsync(s.mult.p, size_t(nb) * 8, multipliers + b0, size_t(n_members) * 8, size_t(nb) * 8,
+                             size_t(n_ops), cudaMemcpyHostToDevice, s.stream));
+      CK(cudaMemsetAsync(s.g.p, 0, size_t(max_gradient) * size_t(K) * 8, s.stream));
+      batch_seed_kernel<<<unsigned((nb * D + 255) / 256), 256, 0, s.stream>>>(s.g.as<double>(), K, s.seed_slots.as<int32_t>(),
+                                                                            int(D), Dp, nb);
+      s.launches += 1;
+      if (R > 0) {
+        ReplayArgs A{};
+        A.recs = (mode == 0 ? s.fwd_t : s.rev_t).as<Rec>();
+        A.chunk_begin = s.one_chunk.as<int64_t>();
+        A.first_chunk = 0;
+        A.g = s.g.as<double>();
+        A.K = K;
+        A.n_colblocks = int(K / 32);
+        A.n_dirs = lanes;
+        A.ref_block = P;
+        A.bmult = s.mult.as<double>();
+        A.n_members = nb;
+        A.dirs_padded = Dp;
+        const int warps = 8;
+        const unsigned gy = unsigned((A.n_colblocks + warps - 1) / warps);
+        if (mode == 0) replay_forward_kernel<true, true><<<dim3(1, gy), warps * 32, 0, s.stream>>>(A);
+        else replay_reverse_kernel<true><<<dim3(1, gy), warps * 32, 0, s.stream>>>(A);
+        s.launches += 1;
+      }
+      const int64_t total = nb * n_out * D;
+      batch_extract_kernel<<<unsigned((total + 255) / 256), 256, 0, s.stream>>>(
+          s.g.as<double>(), K, s.out_slots.as<int32_t>(), int(n_out), int(D), Dp, nb, mode, n_dep, n_indep,
+          s.out.as<double>());
+      s.launches += 1;
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(jac_out_host + b0 * n_dep * n_indep, s.out.p, size_t(nb) * n_dep * n_indep * 8,
+                         cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+    }
+    return 0;
+  }));
+  c->stat["batch_wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  c->stat["kernel_launches"] = c->total_launches();
+  return 0;
 }
 
 int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {

@@ -41,6 +41,11 @@ struct ReplayArgs {
   int n_colblocks;             // 32-lane column blocks in this pass
   int64_t n_dirs;              // directions resident in this pass (lanes beyond are masked)
   int ref_block;               // P of the reference's skip test (reverse only)
+  // ensemble mode (adept_cuda_jacobian_batch): lane L = member*dirs_padded + direction; the record's m field
+  // holds the OPERATION INDEX and the multiplier is per member: bmult[op*n_members + member]
+  const double* bmult;
+  int64_t n_members;
+  int dirs_padded;
 };
 
 struct StageRing {
@@ -63,7 +68,7 @@ __device__ __forceinline__ void issue_piece(StageRing& ring, const Rec* chunk, i
 // a chunk may depend on each other: the tape-ordered schedule).  CHECK=false is for level
 // chunks, where no OP reads a slot that any TAIL of the same level writes.
 // ---------------------------------------------------------------------------------------
-template <bool CHECK>
+template <bool CHECK, bool BATCH>
 __global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {
   __shared__ StageRing ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,6 +82,8 @@ __global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {
   const bool live = cb < A.n_colblocks;
   const bool lane_ok = static_cast<int64_t>(cb) * 32 + lane < A.n_dirs;
   double* gcol = A.g + static_cast<int64_t>(cb) * 32 + lane;
+  const double* mcol = nullptr;  // ensemble mode: this lane's member column of the multiplier matrix
+  if (BATCH && lane_ok) mcol = A.bmult + (static_cast<int64_t>(cb) * 32 + lane) / A.dirs_padded;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
@@ -119,7 +126,9 @@ __global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {
                 for (int w = 0; w < u; ++w)
                   if (rc[w].kind == REC_MARK && rc[w].slot == rc[u].slot) x = stv[w];
               }
-              acc = mul_add_rn(acc, rc[u].m, x);
+              double m = rc[u].m;
+              if (BATCH) m = lane_ok ? mcol[__double_as_longlong(rc[u].m) * A.n_members] : 0.0;
+              acc = mul_add_rn(acc, m, x);
             }
           } else {  // TAIL: the statement is complete
             if (lane_ok) gcol[static_cast<int64_t>(rc[u].slot) * A.K] = acc;
@@ -140,6 +149,7 @@ __global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {
 // only when ALL lanes of the block are zero; otherwise all lanes are updated).  Forwarding is
 // always on: a statement may name one slot several times, or its own LHS.
 // ---------------------------------------------------------------------------------------
+template <bool BATCH>
 __global__ void __launch_bounds__(256) replay_reverse_kernel(ReplayArgs A) {
   __shared__ StageRing ring;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,6 +163,8 @@ __global__ void __launch_bounds__(256) replay_reverse_kernel(ReplayArgs A) {
   const bool live = cb < A.n_colblocks;
   const bool lane_ok = static_cast<int64_t>(cb) * 32 + lane < A.n_dirs;
   double* gcol = A.g + static_cast<int64_t>(cb) * 32 + lane;
+  const double* mcol = nullptr;
+  if (BATCH && lane_ok) mcol = A.bmult + (static_cast<int64_t>(cb) * 32 + lane) / A.dirs_padded;
   // lanes of my reference block: P consecutive directions, P | 32
   const uint32_t P = static_cast<uint32_t>(A.ref_block);
   const uint32_t grp_mask = (P >= 32 ? 0xffffffffu : ((1u << P) - 1u)) << ((lane / P) * P);
@@ -203,7 +215,9 @@ __global__ void __launch_bounds__(256) replay_reverse_kernel(ReplayArgs A) {
             if (lane_ok) *dst = 0.0;
           } else {
             if (act) {
-              x = mul_add_rn(x, rc[u].m, a);
+              double m = rc[u].m;
+              if (BATCH) m = lane_ok ? mcol[__double_as_longlong(rc[u].m) * A.n_members] : 0.0;
+              x = mul_add_rn(x, m, a);
               if (lane_ok) *dst = x;
             }
             v[u] = x;
@@ -464,6 +478,33 @@ __global__ void extract_kernel(const double* __restrict__ g, int64_t K, const in
       if (i < n_out && j < n_dirs) out[i * stride_i + (d0 + j) * stride_j] = tile[r][threadIdx.x];
     }
   }
+}
+
+// Ensemble seeding/extraction.  Lane L = b*Dp + d (b member, d direction, Dp = directions padded to the
+// reference block).  Output per member is the reference's default column-major n_dep x n_indep layout.
+__global__ void batch_seed_kernel(double* g, int64_t K, const int32_t* seed_slot, int n_dirs, int Dp, int64_t n_members) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_members * n_dirs) return;
+  const int64_t b = t / n_dirs;
+  const int d = static_cast<int>(t - b * n_dirs);
+  g[static_cast<int64_t>(seed_slot[d]) * K + b * Dp + d] = 1.0;
+}
+// mode 0 (forward): directions are independents j, outputs are dependents i; mode 1: the other way round.
+__global__ void batch_extract_kernel(const double* __restrict__ g, int64_t K, const int32_t* __restrict__ out_slot,
+                                     int n_out, int n_dirs, int Dp, int64_t n_members, int mode, int64_t n_dep,
+                                     int64_t n_indep, double* __restrict__ out) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per = static_cast<int64_t>(n_out) * n_dirs;
+  if (t >= n_members * per) return;
+  // consecutive threads: direction fastest, then member (coalesced reads of a gradient row), then out index
+  const int64_t o = t / (n_members * n_dirs);
+  const int64_t rem = t - o * n_members * n_dirs;
+  const int64_t b = rem / n_dirs;
+  const int d = static_cast<int>(rem - b * n_dirs);
+  const double v = g[static_cast<int64_t>(out_slot[o]) * K + b * Dp + d];
+  const int64_t i = mode == 0 ? o : d;  // dependent index
+  const int64_t j = mode == 0 ? d : o;  // independent index
+  out[b * n_dep * n_indep + i + j * n_dep] = v;
 }
 
 }  // namespace adept_b200

@@ -63,7 +63,7 @@ __global__ void build_streams_kernel(const int2* __restrict__ stmt, int64_t n_st
   for (int64_t o = t; o < n_ops; o += stride) {
     const int64_t s = stmt_of_op(stmt, n_stmt, o);
     Rec r;
-    r.m = mult[o];
+    r.m = mult ? mult[o] : __longlong_as_double(o);  // ensemble mode: the record carries the operation index
     r.slot = idx[o];
     r.kind = REC_OP;
     const int64_t fpos = o + (s - 1);

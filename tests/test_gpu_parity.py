@@ -275,3 +275,30 @@ def test_stack_api(pkg, po):
     assert s2.jacobian().tolist() == [2.0, 3.0]
     s2.push_rhs(10.0, y); s2.push_lhs(y)                          # y *= 10
     assert s2.jacobian().tolist() == [20.0, 30.0]
+
+
+# ---- ensembles: B tapes sharing one structure (BASELINE config 3: simulate_radiances x 1e5 members) ----
+@pytest.mark.parametrize("B", [1, 37, 1000])
+def test_ensemble_jacobians(engine, po, pkg, B):
+    """test/simulate_radiances.cpp:52-146 records the same 54-statement structure for every state vector;
+    members differ only in their multipliers ([op][member]).  Each member's 2x26 Jacobian must equal the
+    oracle's for that member's tape, bit for bit, in both sweep directions."""
+    t = pkg.tapegen.radiance_tape()
+    rng = np.random.default_rng(B)
+    mm = t["mult"][:, None] * (1.0 + 0.05 * rng.standard_normal((t["mult"].size, B)))
+    for mode in (1, 0):
+        got = engine.jacobian_batch(mode, t["stmt"], t["idx"], t["max_gradient"], mm, t["indep"], t["dep"])
+        assert got.shape == (B, t["indep"].size, t["dep"].size)
+        for b in ([0] if B == 1 else list(rng.integers(0, B, 12)) + [0, B - 1]):
+            rc, want = po.jacobian(t["stmt"], np.ascontiguousarray(mm[:, b]), t["idx"], t["max_gradient"], t["indep"],
+                                   t["dep"], mode)
+            assert rc == 0 and same_bits(got[b], want), (mode, b)
+    # an adversarial structure too (self references, repeated operands, empty statements), odd direction counts
+    r = pkg.tapegen.random_small_tape(np.random.default_rng(9), 200, 30, n_indep=5, n_dep=3)
+    mm = r["mult"][:, None] * rng.uniform(0.5, 1.5, (r["mult"].size, 9))
+    for mode in (0, 1):
+        got = engine.jacobian_batch(mode, r["stmt"], r["idx"], r["max_gradient"], mm, r["indep"], r["dep"])
+        for b in range(9):
+            rc, want = po.jacobian(r["stmt"], np.ascontiguousarray(mm[:, b]), r["idx"], r["max_gradient"], r["indep"],
+                                   r["dep"], mode)
+            assert rc == 0 and same_bits(got[b], want), (mode, b)
