@@ -581,6 +581,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     }
   } else {
     // reverse: steps downwards; per step snapshot a_s and zero the LHS slots, then gather per target
+    constexpr int V = 2;   // a lane owns two adjacent directions: 16-byte row accesses
     TargetArgs B;
     B.recs = s.tgt.as<Rec>();
     B.chunk_begin = s.tchunk.as<int64_t>();
@@ -589,22 +590,24 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     B.rowact = s.rowact.as<uint8_t>();
     B.aflag = s.aflag.as<uint8_t>();
     B.K = K;
-    B.n_colblocks = A.n_colblocks;
-    B.flag_pitch = int(K / 32);
+    B.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
+    B.flag_pitch = int(K / (32 * V));
     B.n_dirs = n_dirs;
     B.ref_block = c->opt_ref_block;
+    const int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
+    const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
     for (int32_t l = s.n_levels; l >= 1; --l) {
       const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
       if (n <= 0) continue;
-      reverse_snapshot_kernel<<<unsigned((n * A.n_colblocks + 255) / 256), 256, 0, s.stream>>>(
+      reverse_snapshot_kernel<V><<<unsigned((n * B.n_colblocks + 255) / 256), 256, 0, s.stream>>>(
           s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
-          s.aflag.as<uint8_t>(), int(K / 32), A.n_colblocks);
+          s.aflag.as<uint8_t>(), B.flag_pitch, B.n_colblocks);
       s.launches += 1;
       const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
       if (c1 > c0) {
         B.first_chunk = c0;
         if (c->opt_time_kernels) RET(mark(s));
-        reverse_target_kernel<<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(B);
+        reverse_target_kernel<V><<<dim3(unsigned(c1 - c0), tgy), twarps * 32, 0, s.stream>>>(B);
         if (c->opt_time_kernels) RET(mark(s));
         s.launches += 1;
       }
@@ -640,12 +643,13 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     if (max_dirs < 32) max_dirs = 32;
     int64_t pass = std::min<int64_t>(((D + 31) / 32) * 32, max_dirs);
     if (c->opt_pass_dirs > 0) pass = std::min<int64_t>(pass, ((c->opt_pass_dirs + 31) / 32) * 32);
-    const int64_t K = pass;
+    const int64_t K = ((pass + 63) / 64) * 64;   // rows padded so that 16-byte lane vectors never leave a row
     RET(ensure(errp, s.g, size_t(s.max_gradient) * size_t(K) * 8));
     double* g = s.g.as<double>();
     int n_passes = 0;
     const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
-    const int ncb_pass = int(K / 32);
+    const int V = 2;                               // doubles per lane in the level-reverse kernels
+    const int ncb_pass = int(K / (32 * V));
     const bool sparse = plan.use_levels && mode == 1;
     if (sparse) {
       RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
@@ -658,7 +662,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       CK(cudaMemsetAsync(g, 0, size_t(s.max_gradient) * size_t(K) * 8, s.stream));
       if (sparse) CK(cudaMemsetAsync(s.rowact.p, 0, size_t(s.max_gradient) * size_t(ncb_pass), s.stream));
       seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n),
-                                                                    sparse ? s.rowact.as<uint8_t>() : nullptr, ncb_pass);
+                                                                    sparse ? s.rowact.as<uint8_t>() : nullptr, ncb_pass, 32 * V);
       s.launches += 1;
       if (last) CK(cudaEventRecord(s.ev[2], s.stream));
       RET(launch_sweep(c, s, mode, g, K, n, plan));

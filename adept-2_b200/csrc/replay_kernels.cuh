@@ -247,8 +247,33 @@ __global__ void __launch_bounds__(256) replay_reverse_kernel(ReplayArgs A) {
 //   aflag[k*ncb + cb]     == 0  =>  the snapshot a_s of statement k is all zero in that block
 // A zero block contributes exactly nothing in the reference either (the whole block is zero, so
 // every P-lane sub-block is skipped), so eliding its loads, arithmetic and stores keeps all bits.
+// V = doubles per lane (1 or 2).  With V = 2 a lane owns two adjacent directions and every row access is
+// a 16-byte vector load/store (512 bytes per warp): twice the bytes in flight per warp for the same
+// instruction count.  A "column block" is 32*V directions; rowact/aflag have one byte per block.
+template <int V>
+struct LaneVec;
+template <>
+struct LaneVec<1> {
+  double x;
+  __device__ __forceinline__ void load(const double* p) { x = *p; }
+  __device__ __forceinline__ void store(double* p) const { *p = x; }
+  __device__ __forceinline__ void zero() { x = 0.0; }
+};
+template <>
+struct LaneVec<2> {
+  double x, y;
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    x = t.x;
+    y = t.y;
+  }
+  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+  __device__ __forceinline__ void zero() { x = 0.0; y = 0.0; }
+};
+
 // One thread looks at one (statement, column block) pair; the active pairs of the CTA are
-// compacted in shared memory and moved one 256-byte row per warp.
+// compacted in shared memory and moved one row segment per warp.
+template <int V>
 __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __restrict__ sched_lhs, int64_t j0,
                                                                int64_t n_stmts, double* __restrict__ g,
                                                                double* __restrict__ abuf, int64_t K, int64_t n_dirs,
@@ -278,14 +303,18 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
     const int64_t k = t / ncb_live;
     const int cb = static_cast<int>(t - k * ncb_live);
     const int64_t lhs = sched_lhs[j0 + k];
-    const int64_t d = static_cast<int64_t>(cb) * 32 + lane;
-    const bool ok = d < n_dirs;
+    const int64_t d = (static_cast<int64_t>(cb) * 32 + lane) * V;   // rows are padded to K: always in bounds
     double* p = g + lhs * K + d;
-    const double a = ok ? *p : 0.0;
-    const bool any = __ballot_sync(0xffffffffu, a != 0.0) != 0u;
-    if (any && ok) {
-      abuf[k * K + d] = a;
-      *p = 0.0;
+    LaneVec<V> a;
+    a.load(p);
+    bool nzl = (a.x != 0.0) && (d < n_dirs);
+    if (V == 2) nzl = nzl || ((reinterpret_cast<const double*>(&a)[V - 1] != 0.0) && (d + 1 < n_dirs));
+    const bool any = __ballot_sync(0xffffffffu, nzl) != 0u;
+    if (any) {
+      a.store(abuf + k * K + d);
+      LaneVec<V> z;
+      z.zero();
+      z.store(p);
     }
     if (lane == 0) {
       aflag[k * pitch + cb] = any ? 1 : 0;
@@ -304,7 +333,7 @@ struct TargetArgs {
   const uint8_t* aflag;
   int64_t K;
   int n_colblocks;   // live column blocks of this pass
-  int flag_pitch;    // row pitch of rowact/aflag (K/32)
+  int flag_pitch;    // row pitch of rowact/aflag
   int64_t n_dirs;
   int ref_block;
 };
@@ -313,6 +342,7 @@ struct TargetArgs {
 // record of the staged piece (pf); a warp whose column block has no active contribution in the
 // piece skips it outright, so dead (target, column block) pairs cost no gradient traffic.
 // (3 CTAs of 8 warps per SM: at 4 the register cap forces spills into the inner loop, measured 20% slower)
+template <int V>
 __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
   __shared__ StageRing ring;
   __shared__ uint8_t pf[kPieceRecs][8];
@@ -327,12 +357,17 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
   const int cb = cb0 + warp;
   const int ncb = A.flag_pitch;
   const bool live = cb < A.n_colblocks;
-  const bool lane_ok = static_cast<int64_t>(cb) * 32 + lane < A.n_dirs;
-  double* gcol = A.g + static_cast<int64_t>(cb) * 32 + lane;
-  const double* acol = A.abuf + static_cast<int64_t>(cb) * 32 + lane;
+  const int64_t d0 = (static_cast<int64_t>(cb) * 32 + lane) * V;  // first direction of this lane; rows are padded to K
+  const bool ok0 = d0 < A.n_dirs, ok1 = d0 + 1 < A.n_dirs;
+  double* gcol = A.g + d0;
+  const double* acol = A.abuf + d0;
   uint8_t* ract = A.rowact + cb;
+  // the reference's P-lane block of my direction(s): with V = 2 and P >= 2 a block is P/2 lanes
   const uint32_t P = static_cast<uint32_t>(A.ref_block);
-  const uint32_t grp_mask = (P >= 32 ? 0xffffffffu : ((1u << P) - 1u)) << ((lane / P) * P);
+  const uint32_t lanes_per_grp = (V == 2) ? (P >= 2 ? P / 2 : 1) : P;
+  const uint32_t grp_mask =
+      (lanes_per_grp >= 32 ? 0xffffffffu : ((1u << lanes_per_grp) - 1u)) << ((lane / lanes_per_grp) * lanes_per_grp);
+  const bool per_component = (V == 2 && P == 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
@@ -342,7 +377,8 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
   if (threadIdx.x == 0)
     for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
 
-  double acc = 0.0;
+  LaneVec<V> acc;
+  acc.zero();
   int32_t cur = -1;        // slot whose sum is (or will be) in acc
   bool acc_valid = false;  // acc holds g[cur] (+ contributions)
   bool dirty = false;      // acc differs from what memory holds
@@ -370,7 +406,7 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
       if (!__any_sync(0xffffffffu, mine)) {
         // nothing to add: retire the open target; remember the last HEAD for a group that goes on
         if (dirty) {
-          if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+          acc.store(gcol + static_cast<int64_t>(cur) * A.K);
           if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
           dirty = false;
         }
@@ -384,43 +420,53 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
         }
       } else {
         for (int i = 0; i < n; i += kBatch) {
-          Rec rc[kBatch];
-          double v[kBatch];
-          uint8_t f[kBatch];
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            if (i + u < n) { rc[u] = r[i + u]; f[u] = pf[i + u][warp]; }
-            else { rc[u].m = 0.0; rc[u].slot = -1; rc[u].kind = REC_OP; f[u] = 0; }
-          }
+          LaneVec<V> v[kBatch];
           // data of the active records only; all loads of a step are independent of its stores
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
-            v[u] = 0.0;
-            if (f[u] && lane_ok)
-              v[u] = (rc[u].kind == REC_MARK) ? gcol[static_cast<int64_t>(rc[u].slot) * A.K]
-                                              : acol[static_cast<int64_t>(rc[u].slot) * A.K];
+            v[u].zero();
+            if (i + u < n && pf[i + u][warp]) {
+              const int32_t slot = r[i + u].slot;
+              v[u].load(((r[i + u].kind == REC_MARK) ? gcol : acol) + static_cast<int64_t>(slot) * A.K);
+            }
           }
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
-            if (rc[u].slot < 0) continue;
-            if (rc[u].kind == REC_MARK) {  // next target: retire the previous one
+            if (i + u >= n) break;
+            const Rec rc = r[i + u];   // re-read from shared memory: keeps the batch's registers for data
+            if (rc.kind == REC_MARK) {  // next target: retire the previous one
               if (dirty) {
-                if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+                acc.store(gcol + static_cast<int64_t>(cur) * A.K);
                 if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
               }
-              cur = rc[u].slot;
+              cur = rc.slot;
               acc = v[u];  // +0.0 when the row is inactive
               acc_valid = true;
               dirty = false;
-            } else if (f[u]) {
+            } else if (pf[i + u][warp]) {
               if (!acc_valid) {  // the group began in a piece this warp skipped
-                acc = 0.0;
-                if (ract[static_cast<int64_t>(cur) * ncb] && lane_ok) acc = gcol[static_cast<int64_t>(cur) * A.K];
+                acc.zero();
+                if (ract[static_cast<int64_t>(cur) * ncb]) acc.load(gcol + static_cast<int64_t>(cur) * A.K);
                 acc_valid = true;
               }
-              const double a = v[u];
-              const uint32_t nz = __ballot_sync(0xffffffffu, a != 0.0);
-              if ((nz & grp_mask) != 0u) acc = mul_add_rn(acc, rc[u].m, a);
+              if (V == 1) {
+                const uint32_t nz = __ballot_sync(0xffffffffu, ok0 && v[u].x != 0.0);
+                if ((nz & grp_mask) != 0u) acc.x = mul_add_rn(acc.x, rc.m, v[u].x);
+              } else {
+                double* av = reinterpret_cast<double*>(&v[u]);
+                double* cv = reinterpret_cast<double*>(&acc);
+                const bool n0 = ok0 && av[0] != 0.0, n1 = ok1 && av[V - 1] != 0.0;
+                bool act0, act1;
+                if (per_component) {
+                  act0 = n0;
+                  act1 = n1;
+                } else {
+                  const uint32_t nz = __ballot_sync(0xffffffffu, n0 || n1);
+                  act0 = act1 = (nz & grp_mask) != 0u;
+                }
+                if (act0) cv[0] = mul_add_rn(cv[0], rc.m, av[0]);
+                if (act1) cv[V - 1] = mul_add_rn(cv[V - 1], rc.m, av[V - 1]);
+              }
               dirty = true;
             }
           }
@@ -431,7 +477,7 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
     if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
   }
   if (live && dirty) {
-    if (lane_ok) gcol[static_cast<int64_t>(cur) * A.K] = acc;
+    acc.store(gcol + static_cast<int64_t>(cur) * A.K);
     if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
   }
 }
@@ -441,12 +487,12 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
 // ---------------------------------------------------------------------------------------
 // g[seed_slot[d0+j]*K + j] = 1.0 for the n directions of this pass.
 __global__ void seed_kernel(double* g, int64_t K, const int32_t* seed_slot, int64_t d0, int n, uint8_t* rowact,
-                            int ncb) {
+                            int ncb, int block_dirs) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) {
     const int64_t slot = seed_slot[d0 + j];
     g[slot * K + j] = 1.0;
-    if (rowact) rowact[slot * ncb + (j >> 5)] = 1;  // several lanes may store the same 1
+    if (rowact) rowact[slot * ncb + j / block_dirs] = 1;  // several lanes may store the same 1
   }
 }
 
