@@ -62,6 +62,7 @@ struct Shard {
   Buf stmt, mult, idx;
   int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
   bool have_tape = false;
+  bool has_nonfinite = false;  // some multiplier is inf/NaN: forward block-sparsity is then off
   // tape-order streams
   Buf fwd_t, rev_t, one_chunk;
   int64_t R = 0;
@@ -260,12 +261,13 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   RET(ensure(errp, s.scratch, 64));
   CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
   validate_kernel<<<grid_for(std::max(O, s.n_stmt), T, s.sm_count), T, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), O, s.max_gradient, s.scratch.as<int>());
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), s.mult.as<double>(), O, s.max_gradient, s.scratch.as<int>());
   s.launches += 1;
   int flags = 0;
   CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  if (flags)
+  s.has_nonfinite = (flags & 2) != 0;
+  if (flags & 1)
     return fail(errp, ADEPT_CUDA_ERR_RANGE,
                 "malformed tape: a slot index is outside [0,max_gradient) or statement ends are not monotone");
   // 2. tape-order streams
@@ -568,14 +570,25 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     if (c->opt_time_kernels) RET(mark(s));
     s.launches += 1;
   } else if (mode == 0) {
-    A.recs = s.fwd_l.as<Rec>();
-    A.chunk_begin = s.fwd_chunk.as<int64_t>();
+    constexpr int V = 2;
+    ForwardArgs F;
+    F.recs = s.fwd_l.as<Rec>();
+    F.chunk_begin = s.fwd_chunk.as<int64_t>();
+    F.g = g;
+    F.rowact = s.rowact.as<uint8_t>();
+    F.K = K;
+    F.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
+    F.flag_pitch = int(K / (32 * V));
+    const int fwarps = std::max(1, std::min(plan.warps, F.n_colblocks));
+    const unsigned fgy = unsigned((F.n_colblocks + fwarps - 1) / fwarps);
+    const bool sparse = !s.has_nonfinite;
     for (int32_t l = 1; l <= s.n_levels; ++l) {
       const int64_t c0 = s.level_chunk[l], c1 = s.level_chunk[l + 1];
       if (c1 <= c0) continue;
-      A.first_chunk = c0;
+      F.first_chunk = c0;
       if (c->opt_time_kernels) RET(mark(s));
-      replay_forward_kernel<false, false><<<dim3(unsigned(c1 - c0), gy), threads, 0, s.stream>>>(A);
+      if (sparse) forward_level_kernel<V, true><<<dim3(unsigned(c1 - c0), fgy), fwarps * 32, 0, s.stream>>>(F);
+      else forward_level_kernel<V, false><<<dim3(unsigned(c1 - c0), fgy), fwarps * 32, 0, s.stream>>>(F);
       if (c->opt_time_kernels) RET(mark(s));
       s.launches += 1;
     }
@@ -650,9 +663,9 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
     const int V = 2;                               // doubles per lane in the level-reverse kernels
     const int ncb_pass = int(K / (32 * V));
-    const bool sparse = plan.use_levels && mode == 1;
+    const bool sparse = plan.use_levels;
     if (sparse) {
-      RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
+      if (mode == 1) RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
       RET(ensure(errp, s.rowact, size_t(s.max_gradient) * size_t(ncb_pass)));
       RET(ensure(errp, s.aflag, size_t(std::max<int64_t>(s.max_step_width, 1)) * size_t(ncb_pass)));
     }
@@ -1286,7 +1299,7 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
     RET(ensure(errp, s.scratch, 64));
     CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
     validate_kernel<<<grid_for(std::max(n_ops, n_stmt), 256, s.sm_count), 256, 0, s.stream>>>(
-        s.stmt.as<int2>(), n_stmt, s.idx.as<int32_t>(), n_ops, max_gradient, s.scratch.as<int>());
+        s.stmt.as<int2>(), n_stmt, s.idx.as<int32_t>(), nullptr, n_ops, max_gradient, s.scratch.as<int>());
     s.launches += 1;
     int flags = 0;
     CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));

@@ -483,6 +483,121 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Level-scheduled forward sweep (one launch per step): statements of a step are mutually
+// independent gathers, so loads are batched freely.  Same CTA shape, TMA staging, lane vectors
+// and block-sparsity bytes as reverse_target_kernel: a statement whose operand blocks are all
+// zero yields +0.0 -- exactly what the reference computes from finite multipliers -- so it is
+// not evaluated (SPARSE is switched off by the host when the tape holds a non-finite multiplier,
+// because 0*inf must then produce the reference's NaN).
+// ---------------------------------------------------------------------------------------
+struct ForwardArgs {
+  const Rec* recs;             // level-major forward stream: OP* TAIL per statement
+  const int64_t* chunk_begin;
+  int64_t first_chunk;
+  double* g;
+  uint8_t* rowact;
+  int64_t K;
+  int n_colblocks;
+  int flag_pitch;
+};
+
+template <int V, bool SPARSE>
+__global__ void __launch_bounds__(256, 3) forward_level_kernel(ForwardArgs A) {
+  __shared__ StageRing ring;
+  __shared__ uint8_t pf[kPieceRecs][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t c = A.first_chunk + blockIdx.x;
+  const int64_t r0 = A.chunk_begin[c], r1 = A.chunk_begin[c + 1];
+  const int64_t n_recs = r1 - r0;
+  const Rec* chunk = A.recs + r0;
+  const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
+  const int cb0 = blockIdx.y * nwarps;
+  const int cb = cb0 + warp;
+  const int ncb = A.flag_pitch;
+  const bool live = cb < A.n_colblocks;
+  double* gcol = A.g + (static_cast<int64_t>(cb) * 32 + lane) * V;  // rows are padded to K: always in bounds
+  uint8_t* ract = A.rowact + cb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
+
+  LaneVec<V> acc;
+  acc.zero();
+  bool open_active = false;  // the statement being summed has had an active operand
+  for (int64_t p = 0; p < n_pieces; ++p) {
+    const int st = static_cast<int>(p % kStages);
+    mbar_wait(&ring.full[st], static_cast<uint32_t>((p / kStages) & 1));
+    const int64_t left = n_recs - p * kPieceRecs;
+    const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
+    const Rec* r = &ring.buf[st][0];
+    if (SPARSE) {
+      for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
+        const int i = t / nwarps, w = t - i * nwarps;
+        const int32_t slot = r[i].slot;
+        uint8_t f = 0;
+        if (cb0 + w < A.n_colblocks && slot >= 0) f = A.rowact[static_cast<int64_t>(slot) * ncb + cb0 + w];
+        pf[i][w] = f;
+      }
+      __syncthreads();
+    }
+    if (live) {
+      bool work = true;
+      if (SPARSE && !open_active) {  // anything to add or to clear in my column block?
+        bool mine = false;
+        for (int i = lane; i < n; i += 32) mine |= (pf[i][warp] != 0);
+        work = __any_sync(0xffffffffu, mine);
+      }
+      if (work) {
+        for (int i = 0; i < n; i += kBatch) {
+          LaneVec<V> v[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            v[u].zero();
+            if (i + u < n && r[i + u].kind == REC_OP && (!SPARSE || pf[i + u][warp])) {
+              const int32_t slot = r[i + u].slot;
+              if (slot >= 0) v[u].load(gcol + static_cast<int64_t>(slot) * A.K);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (i + u >= n) break;
+            const Rec rc = r[i + u];
+            if (rc.kind == REC_OP) {
+              if (rc.slot >= 0 && (!SPARSE || pf[i + u][warp])) {
+                acc.x = mul_add_rn(acc.x, rc.m, v[u].x);
+                if (V == 2) {
+                  double* cv = reinterpret_cast<double*>(&acc);
+                  cv[V - 1] = mul_add_rn(cv[V - 1], rc.m, reinterpret_cast<const double*>(&v[u])[V - 1]);
+                }
+                open_active = true;
+              }
+            } else {  // TAIL: the statement is complete
+              if (!SPARSE || open_active) {
+                acc.store(gcol + static_cast<int64_t>(rc.slot) * A.K);
+                if (SPARSE && lane == 0) ract[static_cast<int64_t>(rc.slot) * ncb] = 1;
+              } else if (pf[i + u][warp]) {  // result is +0.0 but the row still holds an older value
+                acc.store(gcol + static_cast<int64_t>(rc.slot) * A.K);   // acc is +0.0 here
+                if (lane == 0) ract[static_cast<int64_t>(rc.slot) * ncb] = 0;
+              }
+              acc.zero();
+              open_active = false;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Seeding and extraction (adept/jacobian.cpp:163-190 forward, :372-379 and :434-449 reverse).
 // ---------------------------------------------------------------------------------------
 // g[seed_slot[d0+j]*K + j] = 1.0 for the n directions of this pass.

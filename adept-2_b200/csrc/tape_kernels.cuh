@@ -29,15 +29,16 @@ __device__ __forceinline__ int64_t stmt_of_op(const int2* __restrict__ stmt, int
   return lo;
 }
 
-// flags[0] |= 1 on any malformed entry (slot out of range, ends not monotone).
+// flags[0] |= 1 on any malformed entry (slot out of range, ends not monotone), |= 2 on a non-finite multiplier.
 __global__ void validate_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ idx,
-                                int64_t n_ops, int64_t max_gradient, int* flags) {
+                                const double* __restrict__ mult, int64_t n_ops, int64_t max_gradient, int* flags) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  bool bad = false;
+  bool bad = false, nonfinite = false;
   for (int64_t o = t; o < n_ops; o += stride) {
     const int32_t x = idx[o];
     if (x < 0 || x >= max_gradient) bad = true;
+    if (mult && !isfinite(mult[o])) nonfinite = true;
   }
   for (int64_t s = t; s < n_stmt; s += stride) {
     const int2 st = stmt[s];
@@ -50,6 +51,7 @@ __global__ void validate_kernel(const int2* __restrict__ stmt, int64_t n_stmt, c
     }
   }
   if (bad) atomicOr(flags, 1);
+  if (nonfinite) atomicOr(flags, 2);  // 0*inf must stay NaN: forward sweeps then evaluate every statement
 }
 
 // Tape-order streams.  One thread per record of the forward stream.
