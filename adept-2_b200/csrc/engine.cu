@@ -33,6 +33,7 @@ constexpr int64_t kChunkRecs = 128;          // target records per level chunk (
 constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
+constexpr int64_t kHugeStatement = 65536;       // operands; a longer statement is an analysis window of its own
 constexpr size_t kStageBytes = size_t(32) << 20;
 constexpr size_t kPoolKeepBytes = size_t(8) << 30;  // analysis temporaries kept between uploads up to this size
 
@@ -298,7 +299,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
         for (Buf& b : s.pool) release(b);
     }
   } pool_guard{s};
-  s.pool.resize(24);
+  s.pool.resize(27);
   Buf &cap = s.pool[0], &tab_off = s.pool[1], &tables = s.pool[2], &wdepth = s.pool[3], &wbase = s.pool[4],
       &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &nrec = s.pool[10],
       &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &pos_in_sched = s.pool[15],
@@ -314,31 +315,45 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   };
   // 3. dependency analysis: one warp per window of statements (tape_kernels.cuh)
   const int64_t W = c->opt_window > 0 ? c->opt_window : kDefaultWindow;
-  const int64_t n_windows = (S + W - 1) / W;
+  Buf &wflag = s.pool[24], &wincl = s.pool[25], &win_lo = s.pool[26];
+  RET(ensure(errp, wflag, size_t(s.n_stmt) * 4));
+  RET(ensure(errp, wincl, size_t(s.n_stmt) * 4));
+  window_flags_kernel<<<grid_for(s.n_stmt, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, W,
+                                                                            kHugeStatement, wflag.as<int32_t>());
+  s.launches += 1;
+  RET(inclusive_sum(errp, s, tmp, wflag.as<int32_t>(), wincl.as<int32_t>(), s.n_stmt));
+  int32_t n_windows32 = 0;
+  CK(cudaMemcpyAsync(&n_windows32, wincl.as<int32_t>() + S, 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  const int64_t n_windows = n_windows32;
+  RET(ensure(errp, win_lo, size_t(n_windows + 1) * 8));
+  window_starts_kernel<<<grid_for(s.n_stmt, T, s.sm_count), T, 0, s.stream>>>(wflag.as<int32_t>(), wincl.as<int32_t>(),
+                                                                             s.n_stmt, n_windows, win_lo.as<int64_t>());
+  s.launches += 1;
   RET(ensure(errp, cap, size_t(n_windows + 1) * 8));
   RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
-  window_caps_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, W,
+  window_caps_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), win_lo.as<int64_t>(),
                                                                                 n_windows, cap.as<int64_t>());
   s.launches += 1;
   RET(exclusive_sum(errp, s, tmp, cap.as<int64_t>(), tab_off.as<int64_t>(), n_windows + 1));
   int64_t total_entries = 0;
   CK(cudaMemcpyAsync(&total_entries, tab_off.as<int64_t>() + n_windows, 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  RET(ensure(errp, tables, size_t(total_entries) * sizeof(SlotEntry)));
+  RET(ensure(errp, tables, size_t(std::max<int64_t>(total_entries, 1)) * sizeof(SlotEntry)));
   CK(cudaMemsetAsync(tables.p, 0xFF, size_t(total_entries) * sizeof(SlotEntry), s.stream));
   RET(ensure(errp, s.level, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wdepth, size_t(n_windows + 1) * 4));
   RET(ensure(errp, wbase, size_t(n_windows + 1) * 4));
   CK(cudaMemsetAsync(wdepth.p, 0, size_t(n_windows + 1) * 4, s.stream));
   window_levels_kernel<<<unsigned((n_windows * 32 + 127) / 128), 128, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), W, n_windows, tables.as<SlotEntry>(), tab_off.as<int64_t>(),
-      s.level.as<int32_t>(), wdepth.as<int32_t>());
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, tables.as<SlotEntry>(),
+      tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>());
   s.launches += 1;
   RET(exclusive_sum(errp, s, tmp, wdepth.as<int32_t>(), wbase.as<int32_t>(), n_windows + 1));
   int32_t n_levels = 0;
   CK(cudaMemcpyAsync(&n_levels, wbase.as<int32_t>() + n_windows, 4, cudaMemcpyDeviceToHost, s.stream));
-  global_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), s.n_stmt, W,
-                                                                      wbase.as<int32_t>());
+  global_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), s.n_stmt,
+                                                                      wincl.as<int32_t>(), wbase.as<int32_t>());
   s.launches += 1;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaGetLastError());

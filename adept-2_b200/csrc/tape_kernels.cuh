@@ -113,15 +113,42 @@ struct __align__(16) SlotEntry {
   int32_t rl;   // max step of the readers of the current version (<= 0: none)    } written together
 };
 
-// capacity (power of two >= 2 * touches) of every window's table
-__global__ void window_caps_kernel(const int2* __restrict__ stmt, int64_t n_stmt, int64_t window, int64_t n_windows,
+// Window boundaries.  A window starts every `window` statements, and a statement with more than
+// `huge` operands (e.g. the 4(N-1)-operand `sum` of a cost function, include/adept/reduce.h:162-174) is a
+// window of its own: windows are totally ordered, so such a statement needs no table look-ups at all
+// (its local step is 1) and never stalls the warp that walks its neighbours.
+__global__ void window_flags_kernel(const int2* __restrict__ stmt, int64_t n_stmt, int64_t window, int64_t huge,
+                                    int32_t* __restrict__ flag) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = t; s < n_stmt; s += stride) {
+    int f = 0;
+    if (s >= 1) {
+      const bool big = static_cast<int64_t>(stmt[s].y) - stmt[s - 1].y > huge;
+      const bool prev_big = s >= 2 && static_cast<int64_t>(stmt[s - 1].y) - stmt[s - 2].y > huge;
+      f = ((s - 1) % window == 0) || big || prev_big;
+    }
+    flag[s] = f;
+  }
+}
+// win_lo[w] = first statement of window w (wid = inclusive scan of flag, minus 1); win_lo[n_windows] = n_stmt
+__global__ void window_starts_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ incl, int64_t n_stmt,
+                                     int64_t n_windows, int64_t* __restrict__ win_lo) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = 1 + t; s < n_stmt; s += stride)
+    if (flag[s]) win_lo[incl[s] - 1] = s;
+  if (t == 0) win_lo[n_windows] = n_stmt;
+}
+
+// capacity (power of two >= 2 * touches) of every window's table; a one-statement window needs none
+__global__ void window_caps_kernel(const int2* __restrict__ stmt, const int64_t* __restrict__ win_lo, int64_t n_windows,
                                    int64_t* __restrict__ cap) {
   const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (w > n_windows) return;
   if (w == n_windows) { cap[w] = 0; return; }
-  const int64_t S = n_stmt - 1;
-  const int64_t lo = 1 + w * window;
-  const int64_t hi = (lo + window - 1 < S) ? (lo + window - 1) : S;
+  const int64_t lo = win_lo[w], hi = win_lo[w + 1] - 1;
+  if (lo == hi) { cap[w] = 0; return; }
   const int64_t touches = (static_cast<int64_t>(stmt[hi].y) - stmt[lo - 1].y) + (hi - lo + 1);
   int64_t c = 64;
   while (c < 2 * touches) c <<= 1;
@@ -156,16 +183,23 @@ __device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, i
 }
 
 __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restrict__ stmt, int64_t n_stmt,
-                                                            const int32_t* __restrict__ idx, int64_t window,
+                                                            const int32_t* __restrict__ idx,
+                                                            const int64_t* __restrict__ win_lo,
                                                             int64_t n_windows, SlotEntry* __restrict__ tables,
                                                             const int64_t* __restrict__ tab_off,
                                                             int32_t* __restrict__ level, int32_t* __restrict__ win_depth) {
   const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_windows) return;
-  const int64_t S = n_stmt - 1;
-  const int64_t lo = 1 + w * window;
-  const int64_t hi = (lo + window - 1 < S) ? (lo + window - 1) : S;
+  const int64_t lo = win_lo[w];
+  const int64_t hi = win_lo[w + 1] - 1;
+  if (lo == hi) {  // a window of one statement: step 1, nothing to look up
+    if (lane == 0) {
+      level[lo] = 1;
+      win_depth[w] = 1;
+    }
+    return;
+  }
   SlotEntry* T = tables + tab_off[w];
   const uint32_t mask = static_cast<uint32_t>(tab_off[w + 1] - tab_off[w]) - 1u;
   int32_t depth = 0;
@@ -228,11 +262,11 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
 }
 
 // global step of every statement: step_base[window] + local level
-__global__ void global_steps_kernel(int32_t* __restrict__ level, int64_t n_stmt, int64_t window,
+__global__ void global_steps_kernel(int32_t* __restrict__ level, int64_t n_stmt, const int32_t* __restrict__ wincl,
                                     const int32_t* __restrict__ step_base) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t s = 1 + t; s < n_stmt; s += stride) level[s] += step_base[(s - 1) / window];
+  for (int64_t s = 1 + t; s < n_stmt; s += stride) level[s] += step_base[wincl[s] - 1];
   if (t == 0) level[0] = 0;
 }
 

@@ -169,13 +169,91 @@ def reference_rate(tape, mode, target_seconds=12.0, variant=None):
     return dict(run=run, dirs=dirs, P=P, threads=threads, kind=kind, variant=variant or "sse2", O=O)
 
 
+def side_workload(args, name):
+    """BASELINE configs 5 and 3: not Jacobians of one tape, so they have their own small drivers.
+    Printed in the same JSON shape; `value` is from CUDA events around the device work, `e2e` the whole
+    C-ABI call with host buffers."""
+    import torch
+    pkg = importlib.import_module("adept-2_b200")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    eng = pkg.Engine([0])
+    peak, peak_src = peaks()
+    if name == "rosenbrock1e7":
+        n = 10_000_000
+        t = pkg.tapegen.rosenbrock_tape(n)
+        S, O, G = t["stmt"].shape[0] - 1, t["idx"].size, t["max_gradient"]
+        eng.upload_tape(t["stmt"], t["mult"], t["idx"], G)
+        g0 = np.zeros(G); g0[t["dep"][0]] = 1.0
+        for _ in range(W):
+            out = eng.adjoint(g0)
+        ev, wall = 0.0, 0.0
+        for _ in range(K):
+            t0 = time.perf_counter(); out = eng.adjoint(g0); wall += time.perf_counter() - t0
+            ev += eng.stat("replay_ms") / 1e3
+        want = po.adjoint(t["stmt"], t["mult"], t["idx"], g0)
+        t0 = time.perf_counter(); po.adjoint(t["stmt"], t["mult"], t["idx"], g0); cpu_s = time.perf_counter() - t0
+        rt = None
+        if po.ref_available(po.best_ref_variant()):
+            rt = po.RefTape(po.best_ref_variant()).inject(t["stmt"], t["mult"], t["idx"], G - 1, t["indep"], t["dep"])
+            rt.sweep(True, g0); cpu_s = rt.last_seconds
+        bytes_per_entry = 12 + 8 * S / O + 16 * (1 + S / O)         # SURVEY 8d: 37.6 B for this tape
+        ach = O * bytes_per_entry / (ev / K) / 1e9
+        line = {"metric": "tape entries per second, one compute_adjoint sweep (BASELINE config 5)", "value": O * K / ev,
+                "unit": "entry/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * ev / K,
+                "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: RosenbrockN N=1e7, one level-scheduled compute_adjoint "
+                                       "(4e7 statements / 1e8 operations / 3e7 slots; one statement with 4e7 operands)",
+                           "steps_in_schedule": eng.stat("n_levels"), "analysis_ms": eng.stat("analysis_ms")},
+                "e2e": {"value": O * K / wall, "unit": "entry/s", "h2d_bytes_per_step": G * 8, "d2h_bytes_per_step": G * 8,
+                        "ms_per_step": 1e3 * wall / K},
+                "gpu_launches": int(eng.stat("kernel_launches", 0)),
+                "roofline": {"bound": "hbm", "kernel": "sweep1_snapshot_kernel + sweep1_target_kernel", "achieved": ach,
+                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src},
+                "cpu_baseline": {"value": O / cpu_s, "unit": "entry/s", "cores": 1, "kind": "reference" if rt else "port",
+                                 "sample": "the whole sweep, single-threaded by design (adept/Stack.cpp:139-164)"},
+                "parity_bit_exact_vs_oracle": bool(np.array_equal(out.view(np.uint64), want.view(np.uint64)))}
+    else:  # ensemble1e5
+        B = 100_000
+        t = pkg.tapegen.radiance_tape()
+        O = t["idx"].size
+        rng = np.random.default_rng(0)
+        mm = np.ascontiguousarray(t["mult"][:, None] * (1.0 + 0.01 * rng.standard_normal((O, B))))
+        for _ in range(W):
+            out = eng.jacobian_batch(1, t["stmt"], t["idx"], t["max_gradient"], mm, t["indep"], t["dep"])
+        t0 = time.perf_counter()
+        for _ in range(K):
+            out = eng.jacobian_batch(1, t["stmt"], t["idx"], t["max_gradient"], mm, t["indep"], t["dep"])
+        wall = (time.perf_counter() - t0) / K
+        ok = True
+        t0 = time.perf_counter()
+        for b in range(0, B, B // 500):
+            rc, want = po.jacobian(t["stmt"], np.ascontiguousarray(mm[:, b]), t["idx"], t["max_gradient"], t["indep"], t["dep"], 1)
+            ok &= bool(np.array_equal(out[b].ravel().view(np.uint64), want.view(np.uint64)))
+        cpu_per_member = (time.perf_counter() - t0) / 500
+        work = O * 2.0 * B
+        line = {"metric": "ensemble Jacobians: tape-entry x direction per second (BASELINE config 3)", "value": work / wall,
+                "unit": "op*dir/s", "members_per_s": B / wall, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * wall,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 3: simulate_radiances structure (54 statements / 104 operations / 29 slots), "
+                                       "2x26 reverse Jacobian for an ensemble of 1e5 members; whole call with host buffers"},
+                "e2e": {"value": work / wall, "unit": "op*dir/s", "h2d_bytes_per_step": mm.nbytes, "d2h_bytes_per_step": out.nbytes},
+                "gpu_launches": int(eng.stat("kernel_launches", 0)),
+                "cpu_baseline": {"value": O * 2.0 / cpu_per_member, "unit": "op*dir/s", "cores": 1, "kind": "port",
+                                 "sample": "500 members through the oracle, one at a time (includes Python call overhead)"},
+                "parity_bit_exact_vs_oracle": ok}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="toon4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="toon4096", choices=sorted(WORKLOADS) + ["rosenbrock1e7", "ensemble1e5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--schedule", type=int, default=0)
@@ -183,6 +261,8 @@ def main():
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--warps", type=int, default=8)
     args = ap.parse_args()
+    if args.workload in ("rosenbrock1e7", "ensemble1e5"):
+        return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -166,10 +166,11 @@ int oracle_jacobian_reverse(const int32_t* stmt, int64_t n_stmt, const double* m
              adds the contributions to each slot in (statement descending, operand
              ascending) order then reproduces the reference's accumulation order exactly.
    `window` > 0 restarts the analysis every `window` statements (levels are then local
-   to the window; the schedule is (window, level) lexicographic).  Returns the number of
+   to the window; the schedule is (window, level) lexicographic); with `huge` > 0 a statement
+   of more than `huge` operands is a window of its own.  Returns the number of
    steps (sum of the windows' depths). */
 int64_t oracle_levels(const int32_t* stmt, int64_t n_stmt, const int32_t* idx,
-                      int64_t max_gradient, int mode, int64_t window, int32_t* level) {
+                      int64_t max_gradient, int mode, int64_t window, int64_t huge, int32_t* level) {
   int32_t* wl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* level of last writer  */
   int32_t* rl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* max level of readers of the current version */
   int64_t* ep = (int64_t*)calloc((size_t)max_gradient, sizeof(int64_t)); /* window tag of the entry */
@@ -178,7 +179,13 @@ int64_t oracle_levels(const int32_t* stmt, int64_t n_stmt, const int32_t* idx,
   int64_t cur_win = 1;
   level[0] = 0;
   for (int64_t s = 1; s < n_stmt; ++s) {
-    if (window > 0 && (s - 1) % window == 0 && s > 1) { steps += depth; depth = 0; ++cur_win; }
+    /* a window starts every `window` statements; a statement with more than `huge` operands is a
+       window of its own (so are its neighbours' boundaries) */
+    if (window > 0 && s > 1) {
+      int big = huge > 0 && (END(s) - END(s-1)) > huge;
+      int prev_big = huge > 0 && (END(s-1) - END(s-2)) > huge;
+      if ((s - 1) % window == 0 || big || prev_big) { steps += depth; depth = 0; ++cur_win; }
+    }
 #define TOUCH(x) do { if (ep[x] != cur_win) { ep[x] = cur_win; wl[x] = 0; rl[x] = 0; } } while (0)
     int32_t lv = 0;
     int32_t L = LHS(s);

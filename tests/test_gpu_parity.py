@@ -57,19 +57,22 @@ def test_golden_sweeps(engine, pkg, name, schedule, window):
 @pytest.mark.parametrize("window", [0, 64, 777, 4096])
 def test_levels_match_the_sequential_rule(engine, po, pkg, window):
     for t in (pkg.tapegen.advection_tape("toon", 96, 40), pkg.tapegen.synthetic_tape(30000, 11, 64, seed=5),
-              pkg.tapegen.rosenbrock_tape(3000)):
+              pkg.tapegen.rosenbrock_tape(3000), pkg.tapegen.rosenbrock_tape(18000)):   # the last: a 71996-operand statement
         upload(engine, t, LEVELS, window)
         got = engine.levels()
-        steps, local = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=window or 65536)
-        assert engine.stat("n_levels") == steps
-        # device levels are global step numbers: (window, local level) in lexicographic order
         W = window or 65536
+        steps, local = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=W, huge=65536)
+        assert engine.stat("n_levels") == steps
+        # device levels are global step numbers: (window, local level) in lexicographic order;
+        # a window starts every W statements and around statements of more than 65536 operands
         S = t["stmt"].shape[0] - 1
+        nops = np.diff(t["stmt"][:, 1])                       # nops[s-1] = operands of statement s
+        starts = [s for s in range(1, S + 1)
+                  if (s - 1) % W == 0 or nops[s - 1] > 65536 or (s >= 2 and nops[s - 2] > 65536)] + [S + 1]
         base = 0
-        for w0 in range(1, S + 1, W):
-            seg = slice(w0, min(S + 1, w0 + W))
-            assert np.array_equal(got[seg] - base, local[seg])
-            base += int(local[seg].max())
+        for lo, hi in zip(starts, starts[1:]):
+            assert np.array_equal(got[lo:hi] - base, local[lo:hi])
+            base += int(local[lo:hi].max())
 
 
 # ---- adversarial little tapes: slot reuse, self reference, repeated operands, empty statements -----
