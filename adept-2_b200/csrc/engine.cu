@@ -33,6 +33,7 @@ constexpr int64_t kChunkRecs = 128;          // target records per level chunk (
 constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
+constexpr int64_t kMaxStepWidth = int64_t(1) << 20;  // statements per step (wider steps are split)
 constexpr int64_t kHugeStatement = 65536;       // operands; a longer statement is an analysis window of its own
 constexpr size_t kStageBytes = size_t(32) << 20;
 constexpr size_t kPoolKeepBytes = size_t(8) << 30;  // analysis temporaries kept between uploads up to this size
@@ -299,7 +300,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
         for (Buf& b : s.pool) release(b);
     }
   } pool_guard{s};
-  s.pool.resize(27);
+  s.pool.resize(33);
   Buf &cap = s.pool[0], &tab_off = s.pool[1], &tables = s.pool[2], &wdepth = s.pool[3], &wbase = s.pool[4],
       &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &nrec = s.pool[10],
       &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &pos_in_sched = s.pool[15],
@@ -349,18 +350,68 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, tables.as<SlotEntry>(),
       tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>());
   s.launches += 1;
-  RET(exclusive_sum(errp, s, tmp, wdepth.as<int32_t>(), wbase.as<int32_t>(), n_windows + 1));
+  lap("an_window_ms");
+  // 3b. window packing: local steps -> global steps against a per-slot summary of all earlier windows
   int32_t n_levels = 0;
-  CK(cudaMemcpyAsync(&n_levels, wbase.as<int32_t>() + n_windows, 4, cudaMemcpyDeviceToHost, s.stream));
-  global_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), s.n_stmt,
-                                                                      wincl.as<int32_t>(), wbase.as<int32_t>());
+  Buf &gw = s.pool[27], &gr = s.pool[28], &wopl = s.pool[29], &need = s.pool[31], &gmap = s.pool[32];
+  {
+    RET(exclusive_sum(errp, s, tmp, wdepth.as<int32_t>(), wbase.as<int32_t>(), n_windows + 1));
+    std::vector<int64_t> h_lo(n_windows + 1), h_tab(n_windows + 1), h_op(n_windows + 1);
+    std::vector<int32_t> h_base(n_windows + 1);
+    RET(ensure(errp, wopl, size_t(n_windows + 1) * 8));
+    gather_ends_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), win_lo.as<int64_t>(),
+                                                                                 n_windows + 1, wopl.as<int64_t>());
+    s.launches += 1;
+    CK(cudaMemcpyAsync(h_lo.data(), win_lo.p, size_t(n_windows + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(h_tab.data(), tab_off.p, size_t(n_windows + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(h_op.data(), wopl.p, size_t(n_windows + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(h_base.data(), wbase.p, size_t(n_windows + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    const int64_t total_depth = h_base[n_windows];
+    RET(ensure(errp, gw, size_t(s.max_gradient) * 4));
+    RET(ensure(errp, gr, size_t(s.max_gradient) * 4));
+    RET(ensure(errp, need, size_t(total_depth + 1) * 4));
+    RET(ensure(errp, gmap, size_t(total_depth + 1) * 4));
+    CK(cudaMemsetAsync(gw.p, 0, size_t(s.max_gradient) * 4, s.stream));
+    CK(cudaMemsetAsync(gr.p, 0, size_t(s.max_gradient) * 4, s.stream));
+    CK(cudaMemsetAsync(need.p, 0, size_t(total_depth + 1) * 4, s.stream));
+    for (int64_t w = 0; w < n_windows; ++w) {
+      const int64_t lo = h_lo[w], hi = h_lo[w + 1] - 1, o0 = h_op[w], o1 = h_op[w + 1];
+      const int32_t depth = h_base[w + 1] - h_base[w];
+      int32_t* need_w = need.as<int32_t>() + h_base[w];
+      int32_t* gmap_w = gmap.as<int32_t>() + h_base[w];
+      const int64_t total = (o1 - o0) + (hi - lo + 1);
+      window_need_kernel<<<grid_for(total, T, s.sm_count), T, 0, s.stream>>>(
+          s.stmt.as<int2>(), s.idx.as<int32_t>(), lo, hi, o0, o1, s.level.as<int32_t>(), gw.as<int32_t>(), gr.as<int32_t>(),
+          need_w);
+      window_map_kernel<<<1, 32, 0, s.stream>>>(need_w, depth, gmap_w);
+      if (lo == hi) {
+        window_update_single_ops_kernel<<<grid_for(std::max<int64_t>(o1 - o0, 1), T, s.sm_count), T, 0, s.stream>>>(
+            s.idx.as<int32_t>(), o0, o1, gmap_w, gr.as<int32_t>());
+        window_update_single_lhs_kernel<<<1, 1, 0, s.stream>>>(s.stmt.as<int2>(), lo, gmap_w, gw.as<int32_t>(), gr.as<int32_t>());
+        s.launches += 4;
+      } else {
+        const int64_t cap_w = h_tab[w + 1] - h_tab[w];
+        window_update_kernel<<<grid_for(cap_w, T, s.sm_count), T, 0, s.stream>>>(tables.as<SlotEntry>() + h_tab[w], cap_w, gmap_w,
+                                                                                 gw.as<int32_t>(), gr.as<int32_t>());
+        s.launches += 3;
+      }
+    }
+    std::vector<int32_t> h_map(total_depth + 1);
+    CK(cudaMemcpyAsync(h_map.data(), gmap.p, size_t(total_depth) * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    for (int64_t w = 0; w < n_windows; ++w)
+      if (h_base[w + 1] > h_base[w]) n_levels = std::max(n_levels, h_map[h_base[w + 1] - 1]);
+  }
+  global_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.level.as<int32_t>(), s.n_stmt, wincl.as<int32_t>(),
+                                                                      wbase.as<int32_t>(), gmap.as<int32_t>());
   s.launches += 1;
   CK(cudaStreamSynchronize(s.stream));
   CK(cudaGetLastError());
   s.n_levels = n_levels;
   if (n_levels < 1) return fail(errp, ADEPT_CUDA_ERR_CUDA, "dependency analysis produced no steps");
 
-  lap("an_window_ms");
+  lap("an_pack_ms");
   // 4. statements sorted by step (stable), record offsets, chunk table, level-major forward stream
   const int64_t nmax = std::max(S, O);
   RET(ensure(errp, k0, size_t(nmax) * 4));
@@ -380,6 +431,36 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       s.stmt.as<int2>(), v0.as<uint32_t>(), k0.as<uint32_t>(), S, n_levels, nrec.as<int64_t>(),
       lfirst.as<int64_t>());
   s.launches += 1;
+  {  // steps wider than kMaxStepWidth are cut into sub-steps (bounds the reverse snapshot buffer)
+    std::vector<int64_t> lf(size_t(n_levels) + 2);
+    CK(cudaMemcpyAsync(lf.data(), lfirst.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    int64_t widest = 0;
+    for (int32_t l = 1; l <= n_levels; ++l) widest = std::max(widest, lf[l + 1] - lf[l]);
+    if (widest > kMaxStepWidth) {
+      std::vector<int32_t> nb(size_t(n_levels) + 2, 0);
+      int32_t next = 1;
+      for (int32_t l = 1; l <= n_levels; ++l) {
+        nb[l] = next;
+        next += int32_t((lf[l + 1] - lf[l] + kMaxStepWidth - 1) / kMaxStepWidth);
+      }
+      Buf& nbd = s.pool[30];
+      RET(ensure(errp, nbd, size_t(n_levels + 2) * 4));
+      CK(cudaMemcpyAsync(nbd.p, nb.data(), size_t(n_levels + 2) * 4, cudaMemcpyHostToDevice, s.stream));
+      split_steps_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), v0.as<uint32_t>(), S,
+                                                                         lfirst.as<int64_t>(), nbd.as<int32_t>(),
+                                                                         kMaxStepWidth, s.level.as<int32_t>());
+      s.launches += 1;
+      CK(cudaStreamSynchronize(s.stream));  // nb is a host vector
+      n_levels = next - 1;
+      s.n_levels = n_levels;
+      RET(ensure(errp, lfirst, size_t(n_levels + 2) * 8));
+      sched_sizes_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(
+          s.stmt.as<int2>(), v0.as<uint32_t>(), k0.as<uint32_t>(), S, n_levels, nrec.as<int64_t>(),
+          lfirst.as<int64_t>());
+      s.launches += 1;
+    }
+  }
   RET(exclusive_sum(errp, s, tmp, nrec.as<int64_t>(), s.foff.as<int64_t>(), S + 1));
   RET(ensure(errp, flag, size_t(nmax + 1) * 4));
   RET(ensure(errp, cid, size_t(S + 1) * 4));

@@ -261,12 +261,124 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   if (lane == 0) win_depth[w] = depth;
 }
 
-// global step of every statement: step_base[window] + local level
-__global__ void global_steps_kernel(int32_t* __restrict__ level, int64_t n_stmt, const int32_t* __restrict__ wincl,
-                                    const int32_t* __restrict__ step_base) {
+// ---------------------------------------------------------------------------------------
+// Window packing.  Local steps are turned into global ones by mapping every local step l of a window
+// to a global step g[l], strictly increasing in l and at least the largest lower bound that earlier
+// windows impose on a statement of step l (RAW/WAR/WAW/MONO), summarised per slot in gw (global step
+// of the last writer) and gr (max global step of the readers of the live version).  Windows whose statements do not depend on their predecessors
+// share steps (Rosenbrock: 613 windows -> a handful of steps); dependent ones stack up as before.
+// Windows are visited in order (two small launches each); the work inside a window is parallel.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t stmt_of_op_range(const int2* __restrict__ stmt, int64_t lo, int64_t hi, int64_t o) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (static_cast<int64_t>(stmt[mid].y) > o) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+// need[l-1] = the largest lower bound that earlier windows impose on a statement of local step l
+__global__ void window_need_kernel(const int2* __restrict__ stmt, const int32_t* __restrict__ idx, int64_t lo, int64_t hi,
+                                   int64_t o0, int64_t o1, const int32_t* __restrict__ level,
+                                   const int32_t* __restrict__ gw, const int32_t* __restrict__ gr, int32_t* need) {
+  const int64_t n_ops = o1 - o0, total = n_ops + (hi - lo + 1);
+  for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; t0 < total;
+       t0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = t0 + threadIdx.x;
+    int32_t bound = 0, l = 0;
+    if (t < total) {
+      if (t < n_ops) {
+        const int64_t o = o0 + t;
+        const int64_t s = stmt_of_op_range(stmt, lo, hi, o);
+        const int32_t x = idx[o];
+        bound = max(gw[x] + 1, gr[x]);
+        l = level[s];
+      } else {
+        const int64_t s = lo + (t - n_ops);
+        const int32_t x = stmt[s].x;
+        bound = max(gw[x], gr[x]) + 1;
+        l = level[s];
+      }
+    }
+    // one atomic per warp when the whole warp works on one local step (the common case)
+    const int32_t l0 = __shfl_sync(0xffffffffu, l, 0);
+    if (__all_sync(0xffffffffu, l == l0 || l == 0)) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) bound = max(bound, __shfl_xor_sync(0xffffffffu, bound, d));
+      const int32_t lmax = __reduce_max_sync(0xffffffffu, l);
+      if ((threadIdx.x & 31) == 0 && lmax > 0 && bound > 1) atomicMax(&need[lmax - 1], bound);
+    } else if (l > 0 && bound > 1) {
+      atomicMax(&need[l - 1], bound);
+    }
+  }
+}
+// gmap[l-1] = global step of local step l: strictly increasing, at least need[l-1] (one thread: depth is small)
+__global__ void window_map_kernel(const int32_t* __restrict__ need, int32_t depth, int32_t* __restrict__ gmap) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int32_t prev = 0;
+  for (int32_t l = 0; l < depth; ++l) {
+    const int32_t g = max(need[l], prev + 1);
+    gmap[l] = g;
+    prev = g;
+  }
+}
+// fold the window's final per-slot state (its hash table, local steps) into the global summary
+__global__ void window_update_kernel(const SlotEntry* __restrict__ T, int64_t cap, const int32_t* __restrict__ gmap,
+                                     int32_t* __restrict__ gw, int32_t* __restrict__ gr) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < cap;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const SlotEntry e = T[i];
+    if (e.key < 0) continue;
+    if (e.wl > 0) {  // written in this window: its last writer and the readers after it are what is live now
+      gw[e.key] = gmap[e.wl - 1];
+      gr[e.key] = e.rl > 0 ? gmap[e.rl - 1] : 0;
+    } else if (e.rl > 0) {  // only read: more readers of the version that was already live
+      gr[e.key] = max(gr[e.key], gmap[e.rl - 1]);
+    }
+  }
+}
+// a window of one (huge) statement has no table: its operands are readers at its step ...
+__global__ void window_update_single_ops_kernel(const int32_t* __restrict__ idx, int64_t o0, int64_t o1,
+                                                const int32_t* __restrict__ gmap, int32_t* __restrict__ gr) {
+  const int32_t step = gmap[0];
+  for (int64_t o = o0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < o1;
+       o += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    atomicMax(&gr[idx[o]], step);
+}
+// ... and its LHS is written at that step (after the reads: a self reference reads the old version)
+__global__ void window_update_single_lhs_kernel(const int2* __restrict__ stmt, int64_t s, const int32_t* __restrict__ gmap,
+                                                int32_t* __restrict__ gw, int32_t* __restrict__ gr) {
+  const int32_t lhs = stmt[s].x;
+  gw[lhs] = gmap[0];
+  gr[lhs] = 0;
+}
+// out[w] = first operation of window w (= end of the statement before its first one)
+__global__ void gather_ends_kernel(const int2* __restrict__ stmt, const int64_t* __restrict__ win_lo, int64_t n,
+                                   int64_t* __restrict__ out) {
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w < n) out[w] = stmt[win_lo[w] - 1].y;
+}
+// wide steps are cut into sub-steps of at most `cap` statements (always legal: a step's statements
+// are independent, and the reverse target groups are formed per sub-step in schedule order)
+__global__ void split_steps_kernel(uint32_t* __restrict__ sched_step, const uint32_t* __restrict__ sched_stmt, int64_t S,
+                                   const int64_t* __restrict__ level_first, const int32_t* __restrict__ new_base,
+                                   int64_t cap, int32_t* __restrict__ level) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t s = 1 + t; s < n_stmt; s += stride) level[s] += step_base[wincl[s] - 1];
+  for (int64_t j = t; j < S; j += stride) {
+    const uint32_t l = sched_step[j];
+    const uint32_t nl = static_cast<uint32_t>(new_base[l] + (j - level_first[l]) / cap);
+    sched_step[j] = nl;
+    level[sched_stmt[j]] = static_cast<int32_t>(nl);
+  }
+}
+
+// global step of every statement: gmap[step_base[window] + local step - 1]
+__global__ void global_steps_kernel(int32_t* __restrict__ level, int64_t n_stmt, const int32_t* __restrict__ wincl,
+                                    const int32_t* __restrict__ step_base, const int32_t* __restrict__ gmap) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = 1 + t; s < n_stmt; s += stride) level[s] = gmap[step_base[wincl[s] - 1] + level[s] - 1];
   if (t == 0) level[0] = 0;
 }
 

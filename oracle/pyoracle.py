@@ -55,7 +55,7 @@ def _lib():
         L.oracle_jacobian_forward.restype = C.c_int
         L.oracle_jacobian_reverse.argtypes = jac
         L.oracle_jacobian_reverse.restype = C.c_int
-        L.oracle_levels.argtypes = [_i32p, C.c_int64, _i32p, C.c_int64, C.c_int, C.c_int64, C.c_int64, _i32p]
+        L.oracle_levels.argtypes = [_i32p, C.c_int64, _i32p, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _i32p]
         L.oracle_levels.restype = C.c_int64
         _oracle = L
     return _oracle
@@ -99,12 +99,12 @@ def jacobian(stmt, mult, idx, max_gradient, indep, dep, mode, dep_offset=1, inde
     return rc, out
 
 
-def levels(stmt, idx, max_gradient, mode, window=0, huge=0):
-    """Sequential reference of the device-side dependency analysis. Returns (n_steps, level[])."""
+def levels(stmt, idx, max_gradient, mode, window=0, huge=0, pack=0):
+    """Sequential reference of the device-side dependency analysis. Returns (n_steps, global step of each statement)."""
     stmt = _c(stmt, np.int32).reshape(-1)
     lv = np.zeros(stmt.size // 2, dtype=np.int32)
     steps = _lib().oracle_levels(stmt, stmt.size // 2, _c(idx, np.int32), int(max_gradient), int(mode),
-                                 int(window), int(huge), lv)
+                                 int(window), int(huge), int(pack), lv)
     return int(steps), lv
 
 

@@ -167,49 +167,91 @@ int oracle_jacobian_reverse(const int32_t* stmt, int64_t n_stmt, const double* m
              ascending) order then reproduces the reference's accumulation order exactly.
    `window` > 0 restarts the analysis every `window` statements (levels are then local
    to the window; the schedule is (window, level) lexicographic); with `huge` > 0 a statement
-   of more than `huge` operands is a window of its own.  Returns the number of
+   of more than `huge` operands is a window of its own.  With `pack` every local level of a
+   window is mapped to the smallest global step that respects all earlier windows (summarised
+   per slot) and stays above the window's previous level, so independent windows share steps;
+   without it windows are simply stacked.  level[] holds GLOBAL steps.  Returns the number of
    steps (sum of the windows' depths). */
 int64_t oracle_levels(const int32_t* stmt, int64_t n_stmt, const int32_t* idx,
-                      int64_t max_gradient, int mode, int64_t window, int64_t huge, int32_t* level) {
+                      int64_t max_gradient, int mode, int64_t window, int64_t huge, int pack, int32_t* level) {
   int32_t* wl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* level of last writer  */
   int32_t* rl = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* max level of readers of the current version */
   int64_t* ep = (int64_t*)calloc((size_t)max_gradient, sizeof(int64_t)); /* window tag of the entry */
-  int64_t steps = 0;
-  int32_t depth = 0;
-  int64_t cur_win = 1;
+  int32_t* gw = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* packing: global step of the last writer */
+  int32_t* gr = (int32_t*)calloc((size_t)max_gradient, sizeof(int32_t)); /* packing: max global step of live readers */
+  int64_t steps = 0, base = 0;
+  int64_t cur_win = 0;
   level[0] = 0;
-  for (int64_t s = 1; s < n_stmt; ++s) {
-    /* a window starts every `window` statements; a statement with more than `huge` operands is a
-       window of its own (so are its neighbours' boundaries) */
-    if (window > 0 && s > 1) {
+  int64_t s = 1;
+  while (s < n_stmt) {
+    /* the window [s, e): starts every `window` statements; a statement with more than `huge`
+       operands is a window of its own */
+    int64_t e = s + 1;
+    if (window <= 0) e = n_stmt;
+    else {
       int big = huge > 0 && (END(s) - END(s-1)) > huge;
-      int prev_big = huge > 0 && (END(s-1) - END(s-2)) > huge;
-      if ((s - 1) % window == 0 || big || prev_big) { steps += depth; depth = 0; ++cur_win; }
+      if (!big)
+        while (e < n_stmt && (e - 1) % window != 0 && !(huge > 0 && (END(e) - END(e-1)) > huge)) ++e;
     }
+    ++cur_win;
+    int32_t depth = 0;
 #define TOUCH(x) do { if (ep[x] != cur_win) { ep[x] = cur_win; wl[x] = 0; rl[x] = 0; } } while (0)
-    int32_t lv = 0;
-    int32_t L = LHS(s);
-    TOUCH(L);
-    for (int64_t op = END(s-1); op < END(s); ++op) {
-      int32_t x = idx[op];
-      TOUCH(x);
-      if (wl[x] + 1 > lv) lv = wl[x] + 1;
-      if (mode == 1 && rl[x] + 1 > lv) lv = rl[x] + 1;
-      if (mode == 2 && rl[x] > lv) lv = rl[x];
+    for (int64_t t = s; t < e; ++t) {
+      int32_t lv = 0;
+      int32_t L = LHS(t);
+      TOUCH(L);
+      for (int64_t op = END(t-1); op < END(t); ++op) {
+        int32_t x = idx[op];
+        TOUCH(x);
+        if (wl[x] + 1 > lv) lv = wl[x] + 1;
+        if (mode == 1 && rl[x] + 1 > lv) lv = rl[x] + 1;
+        if (mode == 2 && rl[x] > lv) lv = rl[x];
+      }
+      if (wl[L] + 1 > lv) lv = wl[L] + 1;
+      if (rl[L] + 1 > lv) lv = rl[L] + 1;
+      if (lv < 1) lv = 1;
+      level[t] = lv;
+      for (int64_t op = END(t-1); op < END(t); ++op) {
+        int32_t x = idx[op];
+        if (lv > rl[x]) rl[x] = lv;
+      }
+      /* the write retires the old version (a statement's own reads belong to it) */
+      wl[L] = lv; rl[L] = (mode == 1) ? lv : 0;
+      if (lv > depth) depth = lv;
     }
-    if (wl[L] + 1 > lv) lv = wl[L] + 1;
-    if (rl[L] + 1 > lv) lv = rl[L] + 1;
-    if (lv < 1) lv = 1;
-    level[s] = lv;
-    for (int64_t op = END(s-1); op < END(s); ++op) {
-      int32_t x = idx[op];
-      if (lv > rl[x]) rl[x] = lv;
+    if (!pack) {
+      for (int64_t t = s; t < e; ++t) level[t] += (int32_t)base;
+      if (base + depth > steps) steps = base + depth;
+    } else {
+      /* every local level l of the window gets its own global step g[l], strictly increasing in l:
+         g[l] = max(g[l-1]+1, the largest lower bound earlier windows impose on a statement of level l) */
+      int32_t* g = (int32_t*)calloc((size_t)depth + 1, sizeof(int32_t));
+      for (int64_t t = s; t < e; ++t) {
+        int32_t L = LHS(t), need, l = level[t];
+        for (int64_t op = END(t-1); op < END(t); ++op) {
+          int32_t x = idx[op];
+          need = (gw[x] + 1 > gr[x] ? gw[x] + 1 : gr[x]);
+          if (need > g[l]) g[l] = need;
+        }
+        need = (gw[L] > gr[L] ? gw[L] : gr[L]) + 1;
+        if (need > g[l]) g[l] = need;
+      }
+      for (int32_t l = 1; l <= depth; ++l) if (g[l] < g[l-1] + 1) g[l] = g[l-1] + 1;
+      /* fold the window's final per-slot state into the summary (idempotent per slot) */
+      for (int64_t t = s; t < e; ++t) {
+        for (int64_t op = END(t-1); op <= END(t); ++op) {
+          int32_t x = (op < END(t)) ? idx[op] : LHS(t);
+          if (wl[x] > 0) { gw[x] = g[wl[x]]; gr[x] = rl[x] > 0 ? g[rl[x]] : 0; }
+          else if (rl[x] > 0 && g[rl[x]] > gr[x]) gr[x] = g[rl[x]];
+        }
+      }
+      for (int64_t t = s; t < e; ++t) level[t] = g[level[t]];
+      if (g[depth] > steps) steps = g[depth];
+      free(g);
     }
-    /* the write retires the old version (a statement's own reads belong to it) */
-    wl[L] = lv; rl[L] = (mode == 1) ? lv : 0;
-    if (lv > depth) depth = lv;
+    base += depth;
+    s = e;
   }
-  steps += depth;
-  free(wl); free(rl); free(ep);
+  free(wl); free(rl); free(ep); free(gw); free(gr);
   return steps;
 }

@@ -61,18 +61,9 @@ def test_levels_match_the_sequential_rule(engine, po, pkg, window):
         upload(engine, t, LEVELS, window)
         got = engine.levels()
         W = window or 65536
-        steps, local = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=W, huge=65536)
+        steps, want = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=W, huge=65536, pack=1)
         assert engine.stat("n_levels") == steps
-        # device levels are global step numbers: (window, local level) in lexicographic order;
-        # a window starts every W statements and around statements of more than 65536 operands
-        S = t["stmt"].shape[0] - 1
-        nops = np.diff(t["stmt"][:, 1])                       # nops[s-1] = operands of statement s
-        starts = [s for s in range(1, S + 1)
-                  if (s - 1) % W == 0 or nops[s - 1] > 65536 or (s >= 2 and nops[s - 2] > 65536)] + [S + 1]
-        base = 0
-        for lo, hi in zip(starts, starts[1:]):
-            assert np.array_equal(got[lo:hi] - base, local[lo:hi])
-            base += int(local[lo:hi].max())
+        assert np.array_equal(got, want)     # global step of every statement, windows packed
 
 
 # ---- adversarial little tapes: slot reuse, self reference, repeated operands, empty statements -----

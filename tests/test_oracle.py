@@ -67,6 +67,11 @@ def test_level_rules(po, pkg):
     assert np.all(l0 <= l2) and np.all(l2 <= l1)
     dw, lw = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=500)
     assert dw >= d2
+    dp, lp = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=500, pack=1)
+    assert d2 <= dp <= dw                       # packing windows never beats the global rule, never loses to stacking
+    r = pkg.tapegen.rosenbrock_tape(5000)       # independent windows collapse onto a few steps
+    assert po.levels(r["stmt"], r["idx"], r["max_gradient"], 2, window=512, pack=1)[0] <= 8
+    assert po.levels(r["stmt"], r["idx"], r["max_gradient"], 2, window=512)[0] > 30
 
 
 # ---- against the real reference (oracle/_ref) -------------------------------------------------
