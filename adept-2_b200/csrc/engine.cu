@@ -22,6 +22,7 @@
 #include "../../include/adept_cuda.h"
 #include "common.cuh"
 #include "replay_kernels.cuh"
+#include "persistent_kernels.cuh"
 #include "sweep1_kernels.cuh"
 #include "tape_kernels.cuh"
 
@@ -29,7 +30,7 @@ using namespace adept_b200;
 
 namespace {
 
-constexpr int64_t kChunkRecs = 128;          // target records per level chunk (one CTA's share of a step)
+constexpr int64_t kChunkRecs = 64;           // target records per level chunk (one CTA's share of a step); measured best of 16..256 on Toon nx=4096
 constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
@@ -72,6 +73,7 @@ struct Shard {
   bool have_levels = false;
   Buf level, fwd_l, fwd_chunk, foff, sched_lhs;   // level-major forward stream and its tables
   Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups
+  Buf d_level_first, d_step_tchunk;                // device copies of the step tables (persistent kernel)
   int32_t n_levels = 0;                            // number of steps
   int64_t n_chunks = 0, n_tchunks = 0, n_groups = 0, R_t = 0, max_step_width = 0;
   std::vector<int64_t> level_chunk;   // [n_levels+2] first forward chunk of each step
@@ -103,6 +105,8 @@ struct adept_cuda_ctx {
   int opt_schedule = 0, opt_ref_block = 2, opt_warps = 8;
   int64_t opt_pass_dirs = 0, opt_workspace_bytes = 0, opt_window = 0;
   int opt_time_kernels = 0;
+  int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
+  int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -316,6 +320,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   };
   // 3. dependency analysis: one warp per window of statements (tape_kernels.cuh)
   const int64_t W = c->opt_window > 0 ? c->opt_window : kDefaultWindow;
+  const int64_t chunk_recs = c->opt_chunk_recs > 0 ? c->opt_chunk_recs : kChunkRecs;
   Buf &wflag = s.pool[24], &wincl = s.pool[25], &win_lo = s.pool[26];
   RET(ensure(errp, wflag, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wincl, size_t(s.n_stmt) * 4));
@@ -466,7 +471,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   RET(ensure(errp, cid, size_t(S + 1) * 4));
   CK(cudaMemsetAsync(flag.p, 0, size_t(S + 1) * 4, s.stream));
   chunk_flags_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), k0.as<uint32_t>(), S,
-                                                                     kChunkRecs, flag.as<int32_t>());
+                                                                     chunk_recs, flag.as<int32_t>());
   s.launches += 1;
   RET(exclusive_sum(errp, s, tmp, flag.as<int32_t>(), cid.as<int32_t>(), S + 1));
   int32_t n_chunks32 = 0;
@@ -540,7 +545,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     RET(ensure(errp, stchunk, size_t(n_levels + 2) * 8));
     CK(cudaMemsetAsync(sgroup.p, 0xFF, size_t(n_levels + 2) * 8, s.stream));
     target_chunk_flags_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(
-        s.goff.as<int64_t>(), gstep.as<int32_t>(), n_groups, kChunkRecs, cflag.as<int32_t>(), sgroup.as<int64_t>());
+        s.goff.as<int64_t>(), gstep.as<int32_t>(), n_groups, chunk_recs, cflag.as<int32_t>(), sgroup.as<int64_t>());
     s.launches += 1;
     RET(inclusive_sum(errp, s, tmp, cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups));
     int32_t n_tchunks32 = 0;
@@ -559,6 +564,11 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     CK(cudaStreamSynchronize(s.stream));
   }
 
+  RET(ensure(errp, s.d_level_first, size_t(n_levels + 2) * 8));
+  RET(ensure(errp, s.d_step_tchunk, size_t(n_levels + 2) * 8));
+  CK(cudaMemcpyAsync(s.d_level_first.p, s.level_first.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemcpyAsync(s.d_step_tchunk.p, s.step_tchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
   lap("an_target_ms");
   // 6. long statements (rare): listed for the single-direction forward sweep
   {
@@ -705,6 +715,28 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     B.ref_block = c->opt_ref_block;
     const int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
     const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
+    if (c->opt_persistent && s.n_tchunks > 0) {
+      // one cooperative kernel walks all steps (persistent_kernels.cuh)
+      PersistArgs PA;
+      PA.T = B;
+      PA.sched_lhs = s.sched_lhs.as<int32_t>();
+      PA.level_first = s.d_level_first.as<int64_t>();
+      PA.step_tchunk = s.d_step_tchunk.as<int64_t>();
+      PA.n_levels = s.n_levels;
+      PA.gy = int(tgy);
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reverse_persistent_kernel<V>, twarps * 32, 0));
+      if (per_sm >= 1) {
+        void* args[] = {&PA};
+        if (c->opt_time_kernels) RET(mark(s));
+        CK(cudaLaunchCooperativeKernel((void*)reverse_persistent_kernel<V>, dim3(unsigned(s.sm_count * per_sm)),
+                                       dim3(unsigned(twarps * 32)), args, 0, s.stream));
+        if (c->opt_time_kernels) RET(mark(s));
+        s.launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+      }
+    }
     for (int32_t l = s.n_levels; l >= 1; --l) {
       const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
       if (n <= 0) continue;
@@ -1117,7 +1149,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -1491,6 +1523,11 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
   } else if (k == "workspace_bytes") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
     c->opt_workspace_bytes = value;
+  } else if (k == "chunk_recs") {
+    if (value < 0 || value > 256) return fail(errp, ADEPT_CUDA_ERR_ARG, "chunk_recs must be in 0..256");
+    c->opt_chunk_recs = value;
+  } else if (k == "persistent") {
+    c->opt_persistent = value ? 1 : 0;
   } else if (k == "time_kernels") {
     c->opt_time_kernels = value ? 1 : 0;
   } else if (k == "window") {

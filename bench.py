@@ -260,6 +260,8 @@ def main():
     ap.add_argument("--pass-dirs", type=int, default=0)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--warps", type=int, default=8)
+    ap.add_argument("--persistent", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
     args = ap.parse_args()
     if args.workload in ("rosenbrock1e7", "ensemble1e5"):
         return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
@@ -313,6 +315,8 @@ def main():
     eng.set_option("pass_dirs", args.pass_dirs)
     eng.set_option("window", args.window)
     eng.set_option("warps_per_cta", args.warps)
+    eng.set_option("persistent", args.persistent)
+    eng.set_option("chunk_recs", args.chunk)
 
     def barrier():
         torch.cuda.synchronize()

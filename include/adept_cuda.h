@@ -131,6 +131,10 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
      "workspace_bytes" cap for the direction-major gradient workspace (0 = 60% of free memory)
      "warps_per_cta" replay CTA size in warps (1..8, default 8)
      "window"        statements per dependency-analysis window (0 = default 65536)
+     "chunk_recs"    records per level chunk = one CTA's share of a step (0 = default 64, max 256); takes effect at
+                     the next adept_cuda_upload_tape
+     "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
+                     between steps; 0 (default) = two launches per step (measured faster on B200)
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
 */

@@ -53,6 +53,24 @@ def test_golden_sweeps(engine, pkg, name, schedule, window):
     assert same_bits(engine.adjoint(g["g_ad_in"], True, flags), g["g_ad_out"]), "adjoint"
 
 
+@pytest.mark.parametrize("name", ["toon_nx128_nt20", "synthetic_s3000", "adversarial_2", "rosenbrock_n400"])
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_reverse_level_sweep_per_step_and_persistent(engine, name, persistent):
+    """The level-scheduled reverse sweep exists as two launches per step and as one cooperative kernel
+    with grid-wide barriers; both must reproduce the reference's reverse Jacobian bit for bit."""
+    g = load_golden(name)
+    engine.set_option("persistent", persistent)
+    try:
+        for window in (0, 200):
+            upload(engine, g, LEVELS, window)
+            assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"])
+            engine.set_option("pass_dirs", 64)
+            assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"])
+    finally:
+        engine.set_option("persistent", 0)
+        engine.set_option("pass_dirs", 0)
+
+
 # ---- the device-side dependency analysis ------------------------------------------------------------
 @pytest.mark.parametrize("window", [0, 64, 777, 4096])
 def test_levels_match_the_sequential_rule(engine, po, pkg, window):
