@@ -107,6 +107,7 @@ struct adept_cuda_ctx {
   int opt_time_kernels = 0;
   int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
   int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
+  int opt_snap_rb = 4;
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -740,9 +741,16 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     for (int32_t l = s.n_levels; l >= 1; --l) {
       const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
       if (n <= 0) continue;
-      reverse_snapshot_kernel<V><<<unsigned((n * B.n_colblocks + 255) / 256), 256, 0, s.stream>>>(
-          s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
-          s.aflag.as<uint8_t>(), B.flag_pitch, B.n_colblocks);
+      {
+        const unsigned sg = unsigned((n * B.n_colblocks + 255) / 256);
+#define SNAP(RBV) reverse_snapshot_kernel<V, RBV><<<sg, 256, 0, s.stream>>>( \
+            s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(), \
+            s.aflag.as<uint8_t>(), B.flag_pitch, B.n_colblocks)
+        if (c->opt_snap_rb == 1) SNAP(1);
+        else if (c->opt_snap_rb == 2) SNAP(2);
+        else SNAP(4);
+#undef SNAP
+      }
       s.launches += 1;
       const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
       if (c1 > c0) {
@@ -1523,6 +1531,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
   } else if (k == "workspace_bytes") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
     c->opt_workspace_bytes = value;
+  } else if (k == "snap_rb") {
+    c->opt_snap_rb = int(value);
   } else if (k == "chunk_recs") {
     if (value < 0 || value > 256) return fail(errp, ADEPT_CUDA_ERR_ARG, "chunk_recs must be in 0..256");
     c->opt_chunk_recs = value;

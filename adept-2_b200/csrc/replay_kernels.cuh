@@ -273,7 +273,7 @@ struct LaneVec<2> {
 
 // One thread looks at one (statement, column block) pair; the active pairs of the CTA are
 // compacted in shared memory and moved one row segment per warp.
-template <int V>
+template <int V, int RB>
 __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __restrict__ sched_lhs, int64_t j0,
                                                                int64_t n_stmts, double* __restrict__ g,
                                                                double* __restrict__ abuf, int64_t K, int64_t n_dirs,
@@ -298,27 +298,42 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
   }
   __syncthreads();
   const int n = cnt;
-  for (int q = warp; q < n; q += (blockDim.x >> 5)) {
-    const int64_t t = t0 + list[q];
-    const int64_t k = t / ncb_live;
-    const int cb = static_cast<int>(t - k * ncb_live);
-    const int64_t lhs = sched_lhs[j0 + k];
-    const int64_t d = (static_cast<int64_t>(cb) * 32 + lane) * V;   // rows are padded to K: always in bounds
-    double* p = g + lhs * K + d;
-    LaneVec<V> a;
-    a.load(p);
-    bool nzl = (a.x != 0.0) && (d < n_dirs);
-    if (V == 2) nzl = nzl || ((reinterpret_cast<const double*>(&a)[V - 1] != 0.0) && (d + 1 < n_dirs));
-    const bool any = __ballot_sync(0xffffffffu, nzl) != 0u;
-    if (any) {
-      a.store(abuf + k * K + d);
-      LaneVec<V> z;
-      z.zero();
-      z.store(p);
+  const int nw = blockDim.x >> 5;
+  // RB = row segments in flight per warp
+  for (int q0 = warp * RB; q0 < n; q0 += nw * RB) {
+    LaneVec<V> a[RB];
+    double* p[RB];
+    int64_t kk[RB], ll[RB];
+    int cbs[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      p[u] = nullptr;
+      if (q0 + u < n) {
+        const int64_t t = t0 + list[q0 + u];
+        kk[u] = t / ncb_live;
+        cbs[u] = static_cast<int>(t - kk[u] * ncb_live);
+        ll[u] = sched_lhs[j0 + kk[u]];
+        p[u] = g + ll[u] * K + (static_cast<int64_t>(cbs[u]) * 32 + lane) * V;  // rows are padded to K: in bounds
+        a[u].load(p[u]);
+      }
     }
-    if (lane == 0) {
-      aflag[k * pitch + cb] = any ? 1 : 0;
-      rowact[lhs * pitch + cb] = 0;  // zeroed (or found zero)
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      if (q0 + u >= n) break;
+      const int64_t d = (static_cast<int64_t>(cbs[u]) * 32 + lane) * V;
+      bool nzl = (a[u].x != 0.0) && (d < n_dirs);
+      if (V == 2) nzl = nzl || ((reinterpret_cast<const double*>(&a[u])[V - 1] != 0.0) && (d + 1 < n_dirs));
+      const bool any = __ballot_sync(0xffffffffu, nzl) != 0u;
+      if (any) {
+        a[u].store(abuf + kk[u] * K + d);
+        LaneVec<V> z;
+        z.zero();
+        z.store(p[u]);
+      }
+      if (lane == 0) {
+        aflag[kk[u] * pitch + cbs[u]] = any ? 1 : 0;
+        rowact[ll[u] * pitch + cbs[u]] = 0;  // zeroed (or found zero)
+      }
     }
   }
 }
