@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "replay_kernels.cuh"
 #include "persistent_kernels.cuh"
+#include "smallg_kernels.cuh"
 #include "sweep1_kernels.cuh"
 #include "tape_kernels.cuh"
 
@@ -73,7 +74,7 @@ struct Shard {
   bool have_levels = false;
   Buf level, fwd_l, fwd_chunk, foff, sched_lhs;   // level-major forward stream and its tables
   Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups
-  Buf d_level_first, d_step_tchunk;                // device copies of the step tables (persistent kernel)
+  Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
   int32_t n_levels = 0;                            // number of steps
   int64_t n_chunks = 0, n_tchunks = 0, n_groups = 0, R_t = 0, max_step_width = 0;
   std::vector<int64_t> level_chunk;   // [n_levels+2] first forward chunk of each step
@@ -108,6 +109,7 @@ struct adept_cuda_ctx {
   int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
   int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
   int opt_snap_rb = 4;
+  int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -567,6 +569,8 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
 
   RET(ensure(errp, s.d_level_first, size_t(n_levels + 2) * 8));
   RET(ensure(errp, s.d_step_tchunk, size_t(n_levels + 2) * 8));
+  RET(ensure(errp, s.d_step_group, size_t(n_levels + 2) * 8));
+  CK(cudaMemcpyAsync(s.d_step_group.p, s.step_group.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_level_first.p, s.level_first.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_step_tchunk.p, s.step_tchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaStreamSynchronize(s.stream));
@@ -780,6 +784,59 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
   CK(cudaEventRecord(s.ev[2], s.stream));
   CK(cudaEventRecord(s.ev[3], s.stream));
   s.stat["n_passes"] = 0;
+  // tapes whose gradient list fits shared memory: one CTA per 32/64 directions walks all steps by itself
+  if (D > 0 && c->opt_smallg && s.have_levels && c->opt_schedule != 1 && s.max_step_width < (int64_t(1) << 20)) {
+    const size_t kSmemCap = size_t(200) << 10;
+    auto need = [&](int dc) { return (size_t(s.max_gradient) + (mode == 1 ? size_t(s.max_step_width) : 0)) * size_t(dc) * 8; };
+    int dc = 0;
+    if (need(32) <= kSmemCap) dc = 32;
+    if (need(64) <= kSmemCap && (D + 31) / 32 > 2 * s.sm_count) dc = 64;
+    if (dc) {
+      SmallGArgs G;
+      G.fwd = s.fwd_l.as<Rec>();
+      G.foff = s.foff.as<int64_t>();
+      G.tgt = s.tgt.as<Rec>();
+      G.goff = s.goff.as<int64_t>();
+      G.sched_lhs = s.sched_lhs.as<int32_t>();
+      G.level_first = s.d_level_first.as<int64_t>();
+      G.step_group = s.d_step_group.as<int64_t>();
+      G.n_levels = s.n_levels;
+      G.max_gradient = s.max_gradient;
+      G.seed_slot = seed_slots_dev;
+      G.out_slot = out_slots_dev;
+      G.n_out = n_out;
+      G.d_lo = d_lo;
+      G.d_hi = d_hi;
+      G.d_base = d_base;
+      G.out = out;
+      G.stride_i = stride_i;
+      G.stride_d = stride_d;
+      G.dc = dc;
+      G.max_width = int(s.max_step_width);
+      G.ref_block = c->opt_ref_block;
+      const size_t smem = need(dc);
+      const unsigned grid = unsigned((D + dc - 1) / dc);
+      CK(cudaEventRecord(s.ev[2], s.stream));
+      if (c->opt_time_kernels) RET(mark(s));
+      if (mode == 0) {
+        CK(cudaFuncSetAttribute(smallg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        smallg_kernel<false><<<grid, 512, smem, s.stream>>>(G);
+      } else {
+        CK(cudaFuncSetAttribute(smallg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        smallg_kernel<true><<<grid, 512, smem, s.stream>>>(G);
+      }
+      if (c->opt_time_kernels) RET(mark(s));
+      CK(cudaEventRecord(s.ev[3], s.stream));
+      s.launches += 1;
+      s.stat["pass_dirs"] = double(D);
+      s.stat["n_passes"] = 1;
+      s.stat["used_schedule"] = 3.0;   // level schedule, shared-memory-resident gradients
+      s.stat["warps_per_cta"] = 16;
+      CK(cudaEventRecord(s.ev[1], s.stream));
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   if (D > 0) {
     // pass size from the workspace budget
     size_t free_b = 0, total_b = 0;
@@ -1157,7 +1214,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -1531,6 +1588,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
   } else if (k == "workspace_bytes") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
     c->opt_workspace_bytes = value;
+  } else if (k == "smallg") {
+    c->opt_smallg = value ? 1 : 0;
   } else if (k == "snap_rb") {
     c->opt_snap_rb = int(value);
   } else if (k == "chunk_recs") {

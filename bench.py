@@ -449,8 +449,9 @@ def main():
     roof = None
     if dom_ms and dom_launches:
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "reverse_target_kernel" if (mode == 1 and used == 2) else
-                ("replay_reverse_kernel" if mode == 1 else "replay_forward_kernel"),
+        kname = {(1, 2.0): "reverse_target_kernel<2>", (0, 2.0): "forward_level_kernel<2,sparse>", (1, 1.0): "replay_reverse_kernel",
+                 (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
+        roof = {"bound": "hbm", "kernel": kname.get((mode, used), "?"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "launches_per_step": dom_launches,
                 "algorithmic_bytes_per_launch": dom_bytes / dom_launches,
@@ -476,7 +477,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "statements": S, "operations": O, "slots": G, "directions": D,
                    "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}",
-                   "schedule": {1.0: "tape-ordered", 2.0: "level"}.get(used, "?"),
+                   "schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
                    "steps_in_schedule": eng.stat("n_levels", 0), "pass_dirs": eng.stat("pass_dirs", 0),
                    "n_passes": eng.stat("n_passes", 0),
                    "l2": "inputs larger than L2: tape streams %.0f MB + workspace %.0f MB per step" %

@@ -131,6 +131,8 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
      "workspace_bytes" cap for the direction-major gradient workspace (0 = 60% of free memory)
      "warps_per_cta" replay CTA size in warps (1..8, default 8)
      "window"        statements per dependency-analysis window (0 = default 65536)
+     "smallg"        1 (default) = Jacobians of tapes whose gradient list fits shared memory (max_gradient*32*8 bytes
+                     plus the reverse snapshot <= 200 KB) run in the shared-memory-resident kernel; 0 = never
      "chunk_recs"    records per level chunk = one CTA's share of a step (0 = default 64, max 256); takes effect at
                      the next adept_cuda_upload_tape
      "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
@@ -144,7 +146,7 @@ int  adept_cuda_set_option(adept_cuda_ctx* ctx, const char* key, int64_t value);
    "kernel_launches" (cumulative count of this library's own kernel launches),
    "replay_ms" (CUDA-event time of the last replay: zero-fill+seed+sweep+extract(+gather)),
    "sweep_ms" (the replay kernels alone), "upload_ms", "analysis_ms", "d2h_ms",
-   "used_schedule" (1 ordered / 2 level), "pass_dirs", "n_passes". */
+   "used_schedule" (1 tape-ordered / 2 level / 3 level with shared-memory gradients), "pass_dirs", "n_passes". */
 int  adept_cuda_get_stat(const adept_cuda_ctx* ctx, const char* key, double* value);
 
 /* Copies the per-statement level (1-based; level[0]=0 for the sentinel) of the last
