@@ -307,7 +307,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
         for (Buf& b : s.pool) release(b);
     }
   } pool_guard{s};
-  s.pool.resize(33);
+  s.pool.resize(34);
   Buf &cap = s.pool[0], &tab_off = s.pool[1], &tables = s.pool[2], &wdepth = s.pool[3], &wbase = s.pool[4],
       &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &nrec = s.pool[10],
       &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &pos_in_sched = s.pool[15],
@@ -341,23 +341,39 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   s.launches += 1;
   RET(ensure(errp, cap, size_t(n_windows + 1) * 8));
   RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
-  window_caps_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), win_lo.as<int64_t>(),
-                                                                                n_windows, cap.as<int64_t>());
-  s.launches += 1;
-  RET(exclusive_sum(errp, s, tmp, cap.as<int64_t>(), tab_off.as<int64_t>(), n_windows + 1));
-  int64_t total_entries = 0;
-  CK(cudaMemcpyAsync(&total_entries, tab_off.as<int64_t>() + n_windows, 8, cudaMemcpyDeviceToHost, s.stream));
-  CK(cudaStreamSynchronize(s.stream));
-  RET(ensure(errp, tables, size_t(std::max<int64_t>(total_entries, 1)) * sizeof(SlotEntry)));
-  CK(cudaMemsetAsync(tables.p, 0xFF, size_t(total_entries) * sizeof(SlotEntry), s.stream));
+  // small gradient lists: direct-indexed table in shared memory, dense per-window state for the packing pass
+  const size_t dense_smem = size_t(s.max_gradient) * 8;
+  const bool dense = dense_smem <= (size_t(160) << 10) && size_t(n_windows) * dense_smem <= (size_t(2) << 30);
+  Buf& wstate = s.pool[33];
   RET(ensure(errp, s.level, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wdepth, size_t(n_windows + 1) * 4));
   RET(ensure(errp, wbase, size_t(n_windows + 1) * 4));
   CK(cudaMemsetAsync(wdepth.p, 0, size_t(n_windows + 1) * 4, s.stream));
-  window_levels_kernel<<<unsigned((n_windows * 32 + 127) / 128), 128, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, tables.as<SlotEntry>(),
-      tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>());
-  s.launches += 1;
+  RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
+  if (dense) {
+    RET(ensure(errp, wstate, size_t(n_windows) * dense_smem));
+    CK(cudaFuncSetAttribute(window_levels_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem)));
+    window_levels_smem_kernel<<<unsigned(n_windows), 32, dense_smem, s.stream>>>(
+        s.stmt.as<int2>(), s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, s.max_gradient, wstate.as<int2>(),
+        s.level.as<int32_t>(), wdepth.as<int32_t>());
+    s.launches += 1;
+    CK(cudaMemsetAsync(tab_off.p, 0, size_t(n_windows + 1) * 8, s.stream));
+  } else {
+    RET(ensure(errp, cap, size_t(n_windows + 1) * 8));
+    window_caps_kernel<<<unsigned((n_windows + 1 + T - 1) / T), T, 0, s.stream>>>(s.stmt.as<int2>(), win_lo.as<int64_t>(),
+                                                                                  n_windows, cap.as<int64_t>());
+    s.launches += 1;
+    RET(exclusive_sum(errp, s, tmp, cap.as<int64_t>(), tab_off.as<int64_t>(), n_windows + 1));
+    int64_t total_entries = 0;
+    CK(cudaMemcpyAsync(&total_entries, tab_off.as<int64_t>() + n_windows, 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    RET(ensure(errp, tables, size_t(std::max<int64_t>(total_entries, 1)) * sizeof(SlotEntry)));
+    CK(cudaMemsetAsync(tables.p, 0xFF, size_t(total_entries) * sizeof(SlotEntry), s.stream));
+    window_levels_kernel<<<unsigned((n_windows * 32 + 127) / 128), 128, 0, s.stream>>>(
+        s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, tables.as<SlotEntry>(),
+        tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>());
+    s.launches += 1;
+  }
   lap("an_window_ms");
   // 3b. window packing: local steps -> global steps against a per-slot summary of all earlier windows
   int32_t n_levels = 0;
@@ -399,9 +415,14 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
         window_update_single_lhs_kernel<<<1, 1, 0, s.stream>>>(s.stmt.as<int2>(), lo, gmap_w, gw.as<int32_t>(), gr.as<int32_t>());
         s.launches += 4;
       } else {
-        const int64_t cap_w = h_tab[w + 1] - h_tab[w];
-        window_update_kernel<<<grid_for(cap_w, T, s.sm_count), T, 0, s.stream>>>(tables.as<SlotEntry>() + h_tab[w], cap_w, gmap_w,
-                                                                                 gw.as<int32_t>(), gr.as<int32_t>());
+        if (dense) {
+          window_update_dense_kernel<<<grid_for(s.max_gradient, T, s.sm_count), T, 0, s.stream>>>(
+              wstate.as<int2>() + w * s.max_gradient, s.max_gradient, gmap_w, gw.as<int32_t>(), gr.as<int32_t>());
+        } else {
+          const int64_t cap_w = h_tab[w + 1] - h_tab[w];
+          window_update_kernel<<<grid_for(cap_w, T, s.sm_count), T, 0, s.stream>>>(tables.as<SlotEntry>() + h_tab[w], cap_w,
+                                                                                   gmap_w, gw.as<int32_t>(), gr.as<int32_t>());
+        }
         s.launches += 3;
       }
     }

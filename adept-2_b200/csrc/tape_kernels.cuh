@@ -261,6 +261,103 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   if (lane == 0) win_depth[w] = depth;
 }
 
+// Same analysis for tapes with a SMALL gradient list (max_gradient * 8 bytes fits shared memory, e.g.
+// the 12 287 slots of Toon nx=4096): the per-slot (writer step, reader step) table is a direct-indexed
+// array in shared memory instead of a hash table in L2, which takes the L2 round trip out of every
+// statement.  One warp (= one CTA) per window; the window's final table is written to wstate[w][slot]
+// for the packing pass.
+__global__ void __launch_bounds__(32) window_levels_smem_kernel(const int2* __restrict__ stmt, const int32_t* __restrict__ idx,
+                                                                const int64_t* __restrict__ win_lo, int64_t n_windows,
+                                                                int64_t max_gradient, int2* __restrict__ wstate,
+                                                                int32_t* __restrict__ level,
+                                                                int32_t* __restrict__ win_depth) {
+  extern __shared__ int2 tab[];   // tab[slot] = {writer step, max reader step}; 0 = none
+  const int64_t w = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (w >= n_windows) return;
+  const int64_t lo = win_lo[w];
+  const int64_t hi = win_lo[w + 1] - 1;
+  int2* out = wstate + w * max_gradient;
+  if (lo == hi) {  // a window of one statement: step 1; its table is never read (single-statement update path)
+    if (lane == 0) {
+      level[lo] = 1;
+      win_depth[w] = 1;
+    }
+    return;
+  }
+  for (int64_t i = lane; i < max_gradient; i += 32) tab[i] = make_int2(0, 0);
+  __syncwarp();
+  int32_t depth = 0;
+  int64_t o0 = stmt[lo - 1].y;
+  int2 st = stmt[lo];
+  int2 st_next = (lo < hi) ? stmt[lo + 1] : st;
+  int32_t x_pre = (o0 + lane < st.y) ? idx[o0 + lane] : -1;   // operand of the current statement for this lane
+  for (int64_t s = lo; s <= hi; ++s) {
+    const int64_t o1 = st.y;
+    const int32_t lhs = st.x;
+    const int64_t nops = o1 - o0;
+    // prefetch: statement s+2 and the first 32 operands of statement s+1 (independent of the table work)
+    const int2 st_next2 = (s + 1 < hi) ? stmt[s + 2] : st_next;
+    const int32_t x_next = (s < hi && o1 + lane < st_next.y) ? idx[o1 + lane] : -1;
+    int32_t lv = 1;
+    if (nops < 32) {
+      const int32_t x = (lane < nops) ? x_pre : (lane == nops ? lhs : -1);
+      if (x >= 0) {
+        const int2 e = tab[x];
+        lv = (lane < nops) ? max(e.x + 1, e.y) : max(e.x, e.y) + 1;
+        lv = max(lv, 1);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+      if (lane < nops) tab[x].y = lv;
+      __syncwarp();
+      if (lane == nops) {
+        tab[x] = make_int2(lv, 0);
+        level[s] = lv;
+      }
+    } else {
+      for (int64_t o = o0 + lane; o < o1; o += 32) {
+        const int2 e = tab[idx[o]];
+        lv = max(lv, max(e.x + 1, e.y));
+      }
+      const int2 eL = tab[lhs];
+      lv = max(lv, max(eL.x, eL.y) + 1);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+      __syncwarp();
+      for (int64_t o = o0 + lane; o < o1; o += 32) tab[idx[o]].y = lv;
+      __syncwarp();
+      if (lane == 0) {
+        tab[lhs] = make_int2(lv, 0);
+        level[s] = lv;
+      }
+    }
+    __syncwarp();
+    depth = max(depth, lv);
+    o0 = o1;
+    st = st_next;
+    st_next = st_next2;
+    x_pre = x_next;
+  }
+  for (int64_t i = lane; i < max_gradient; i += 32) out[i] = tab[i];
+  if (lane == 0) win_depth[w] = depth;
+}
+// packing update from a dense window state (see window_update_kernel)
+__global__ void window_update_dense_kernel(const int2* __restrict__ state, int64_t max_gradient,
+                                           const int32_t* __restrict__ gmap, int32_t* __restrict__ gw,
+                                           int32_t* __restrict__ gr) {
+  for (int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; x < max_gradient;
+       x += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int2 e = state[x];
+    if (e.x > 0) {
+      gw[x] = gmap[e.x - 1];
+      gr[x] = e.y > 0 ? gmap[e.y - 1] : 0;
+    } else if (e.y > 0) {
+      gr[x] = max(gr[x], gmap[e.y - 1]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Window packing.  Local steps are turned into global ones by mapping every local step l of a window
 // to a global step g[l], strictly increasing in l and at least the largest lower bound that earlier
