@@ -35,6 +35,7 @@ constexpr int64_t kChunkRecs = 64;           // target records per level chunk (
 constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
 constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
 constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
+constexpr double kWideStepCtas = 4096.0;           // average CTAs per step above which one stream suffices
 constexpr int64_t kMaxStepWidth = int64_t(1) << 20;  // statements per step (wider steps are split)
 constexpr int64_t kHugeStatement = 65536;       // operands; a longer statement is an analysis window of its own
 constexpr size_t kStageBytes = size_t(32) << 20;
@@ -88,6 +89,9 @@ struct Shard {
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
   std::vector<Buf> pool;  // analysis temporaries (build_schedule)
+  std::vector<cudaStream_t> aux;      // extra streams: independent direction ranges of one sweep
+  std::vector<cudaEvent_t> aux_ev;
+  cudaEvent_t fork_ev = nullptr;
   // per-shard bookkeeping (shards may be driven by worker threads)
   std::string err;
   double launches = 0;
@@ -109,6 +113,7 @@ struct adept_cuda_ctx {
   int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
   int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
   int opt_snap_rb = 4;
+  int opt_streams = 4;  // CUDA streams over which the direction ranges of a level-scheduled reverse sweep are spread
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   // stats
   std::map<std::string, double> stat;
@@ -323,7 +328,6 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   };
   // 3. dependency analysis: one warp per window of statements (tape_kernels.cuh)
   const int64_t W = c->opt_window > 0 ? c->opt_window : kDefaultWindow;
-  const int64_t chunk_recs = c->opt_chunk_recs > 0 ? c->opt_chunk_recs : kChunkRecs;
   Buf &wflag = s.pool[24], &wincl = s.pool[25], &win_lo = s.pool[26];
   RET(ensure(errp, wflag, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wincl, size_t(s.n_stmt) * 4));
@@ -441,6 +445,9 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   if (n_levels < 1) return fail(errp, ADEPT_CUDA_ERR_CUDA, "dependency analysis produced no steps");
 
   lap("an_pack_ms");
+  // one CTA's share of a step: 64 records when steps are narrow (shorter critical path per launch), 128 when they
+  // are wide (measured: Toon nx=4096 171 vs 196 ms; synthetic forward 537 vs 462 ms)
+  const int64_t chunk_recs = c->opt_chunk_recs > 0 ? c->opt_chunk_recs : (R / std::max(1, n_levels) >= 32768 ? 2 * kChunkRecs : kChunkRecs);
   // 4. statements sorted by step (stable), record offsets, chunk table, level-major forward stream
   const int64_t nmax = std::max(S, O);
   RET(ensure(errp, k0, size_t(nmax) * 4));
@@ -711,18 +718,67 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     F.K = K;
     F.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
     F.flag_pitch = int(K / (32 * V));
+    F.cb_lo = 0;
     const int fwarps = std::max(1, std::min(plan.warps, F.n_colblocks));
-    const unsigned fgy = unsigned((F.n_colblocks + fwarps - 1) / fwarps);
     const bool sparse = !s.has_nonfinite;
-    for (int32_t l = 1; l <= s.n_levels; ++l) {
-      const int64_t c0 = s.level_chunk[l], c1 = s.level_chunk[l + 1];
-      if (c1 <= c0) continue;
-      F.first_chunk = c0;
-      if (c->opt_time_kernels) RET(mark(s));
-      if (sparse) forward_level_kernel<V, true><<<dim3(unsigned(c1 - c0), fgy), fwarps * 32, 0, s.stream>>>(F);
-      else forward_level_kernel<V, false><<<dim3(unsigned(c1 - c0), fgy), fwarps * 32, 0, s.stream>>>(F);
-      if (c->opt_time_kernels) RET(mark(s));
-      s.launches += 1;
+    // independent direction ranges on separate streams, one issuing host thread each (see the reverse sweep)
+    const int all_cb = F.n_colblocks;
+    const int groups = (all_cb + fwarps - 1) / fwarps;
+    int nstr = std::max(1, std::min<int>(c->opt_streams, groups));
+    // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
+    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= kWideStepCtas || c->opt_time_kernels) nstr = 1;
+    while (int(s.aux.size()) < nstr - 1) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      s.aux.push_back(st);
+      s.aux_ev.push_back(ev);
+    }
+    if (nstr > 1) {
+      CK(cudaEventRecord(s.fork_ev, s.stream));
+      for (int i = 1; i < nstr; ++i) CK(cudaStreamWaitEvent(s.aux[i - 1], s.fork_ev, 0));
+    }
+    std::vector<int> rcs(nstr, 0);
+    std::vector<double> nl(nstr, 0.0);
+    auto run_stream = [&](int i) {
+      if (cudaSetDevice(s.dev) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+      const int g_lo = int(int64_t(groups) * i / nstr), g_hi = int(int64_t(groups) * (i + 1) / nstr);
+      if (g_hi <= g_lo) return;
+      cudaStream_t st = (i == 0) ? s.stream : s.aux[i - 1];
+      ForwardArgs Fi = F;
+      Fi.cb_lo = g_lo * fwarps;
+      Fi.n_colblocks = std::min(all_cb, g_hi * fwarps);
+      for (int32_t l = 1; l <= s.n_levels; ++l) {
+        const int64_t c0 = s.level_chunk[l], c1 = s.level_chunk[l + 1];
+        if (c1 <= c0) continue;
+        Fi.first_chunk = c0;
+        const dim3 grid(unsigned(c1 - c0), unsigned(g_hi - g_lo));
+        if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+        if (sparse) forward_level_kernel<V, true><<<grid, fwarps * 32, 0, st>>>(Fi);
+        else forward_level_kernel<V, false><<<grid, fwarps * 32, 0, st>>>(Fi);
+        if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+        nl[i] += 1;
+      }
+      if (cudaGetLastError() != cudaSuccess) rcs[i] = ADEPT_CUDA_ERR_CUDA;
+    };
+    if (nstr == 1) {
+      run_stream(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 1; i < nstr; ++i) th.emplace_back(run_stream, i);
+      run_stream(0);
+      for (std::thread& t : th) t.join();
+    }
+    for (int i = 0; i < nstr; ++i) {
+      s.launches += nl[i];
+      if (rcs[i]) return fail(errp, rcs[i], "launch failed in the forward level sweep");
+    }
+    if (nstr > 1) {
+      for (int i = 1; i < nstr; ++i) {
+        CK(cudaEventRecord(s.aux_ev[i - 1], s.aux[i - 1]));
+        CK(cudaStreamWaitEvent(s.stream, s.aux_ev[i - 1], 0));
+      }
     }
   } else {
     // reverse: steps downwards; per step snapshot a_s and zero the LHS slots, then gather per target
@@ -739,6 +795,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     B.flag_pitch = int(K / (32 * V));
     B.n_dirs = n_dirs;
     B.ref_block = c->opt_ref_block;
+    B.cb_lo = 0;
     const int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
     const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
     if (c->opt_persistent && s.n_tchunks > 0) {
@@ -763,27 +820,76 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         return 0;
       }
     }
-    for (int32_t l = s.n_levels; l >= 1; --l) {
-      const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
-      if (n <= 0) continue;
-      {
-        const unsigned sg = unsigned((n * B.n_colblocks + 255) / 256);
-#define SNAP(RBV) reverse_snapshot_kernel<V, RBV><<<sg, 256, 0, s.stream>>>( \
-            s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(), \
-            s.aflag.as<uint8_t>(), B.flag_pitch, B.n_colblocks)
-        if (c->opt_snap_rb == 1) SNAP(1);
-        else if (c->opt_snap_rb == 2) SNAP(2);
-        else SNAP(4);
-#undef SNAP
+    // The steps of one direction range are strictly ordered, but direction ranges are independent: split the
+    // column blocks over a few CUDA streams so that the launch gap and the tail of one range's step are filled
+    // by another range's kernels.
+    const int all_cb = B.n_colblocks;
+    int nstr = std::max(1, std::min<int>(c->opt_streams, (all_cb + twarps - 1) / twarps));
+    // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
+    if (double(s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + twarps - 1) / twarps) >= kWideStepCtas ||
+        c->opt_time_kernels)
+      nstr = 1;
+    while (int(s.aux.size()) < nstr - 1) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      s.aux.push_back(st);
+      s.aux_ev.push_back(ev);
+    }
+    if (nstr > 1) {
+      CK(cudaEventRecord(s.fork_ev, s.stream));
+      for (int i = 1; i < nstr; ++i) CK(cudaStreamWaitEvent(s.aux[i - 1], s.fork_ev, 0));
+    }
+    // column groups (of twarps blocks) per stream; one host thread per stream issues that stream's launches
+    // (thousands of small launches per sweep: a single thread would be the bottleneck)
+    const int groups = (all_cb + twarps - 1) / twarps;
+    std::vector<int> rcs(nstr, 0);
+    std::vector<double> nl(nstr, 0.0);
+    auto run_stream = [&](int i) {
+      if (cudaSetDevice(s.dev) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+      const int g_lo = int(int64_t(groups) * i / nstr), g_hi = int(int64_t(groups) * (i + 1) / nstr);
+      if (g_hi <= g_lo) return;
+      const int cb_lo = g_lo * twarps, cb_hi = std::min(all_cb, g_hi * twarps);
+      cudaStream_t st = (i == 0) ? s.stream : s.aux[i - 1];
+      const int ncols = cb_hi - cb_lo;
+      TargetArgs Bi = B;
+      Bi.cb_lo = cb_lo;
+      Bi.n_colblocks = cb_hi;
+      for (int32_t l = s.n_levels; l >= 1; --l) {
+        const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
+        if (n <= 0) continue;
+        const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
+        reverse_snapshot_kernel<V, 4><<<unsigned((n * ncols + 255) / 256), 256, 0, st>>>(
+            s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
+            s.aflag.as<uint8_t>(), B.flag_pitch, ncols, cb_lo);
+        nl[i] += 1;
+        if (c1 > c0) {
+          Bi.first_chunk = c0;
+          if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+          reverse_target_kernel<V><<<dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), twarps * 32, 0, st>>>(Bi);
+          if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+          nl[i] += 1;
+        }
       }
-      s.launches += 1;
-      const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
-      if (c1 > c0) {
-        B.first_chunk = c0;
-        if (c->opt_time_kernels) RET(mark(s));
-        reverse_target_kernel<V><<<dim3(unsigned(c1 - c0), tgy), twarps * 32, 0, s.stream>>>(B);
-        if (c->opt_time_kernels) RET(mark(s));
-        s.launches += 1;
+      if (cudaGetLastError() != cudaSuccess) rcs[i] = ADEPT_CUDA_ERR_CUDA;
+    };
+    if (nstr == 1) {
+      run_stream(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 1; i < nstr; ++i) th.emplace_back(run_stream, i);
+      run_stream(0);
+      for (std::thread& t : th) t.join();
+    }
+    for (int i = 0; i < nstr; ++i) {
+      s.launches += nl[i];
+      if (rcs[i]) return fail(errp, rcs[i], "launch failed in the reverse level sweep: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (nstr > 1) {
+      for (int i = 1; i < nstr; ++i) {
+        CK(cudaEventRecord(s.aux_ev[i - 1], s.aux[i - 1]));
+        CK(cudaStreamWaitEvent(s.stream, s.aux_ev[i - 1], 0));
       }
     }
   }
@@ -1223,6 +1329,7 @@ int init_shard(Shard& s, int dev) {
   CK(cudaSetDevice(dev));
   CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&s.ev[k]));
+  CK(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   s.sm_count = prop.multiProcessorCount;
@@ -1244,6 +1351,9 @@ void free_shard(Shard& s) {
   for (int k = 0; k < 4; ++k)
     if (s.ev[k]) cudaEventDestroy(s.ev[k]);
   for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
+  for (cudaEvent_t e : s.aux_ev) cudaEventDestroy(e);
+  for (cudaStream_t st : s.aux) cudaStreamDestroy(st);
+  if (s.fork_ev) cudaEventDestroy(s.fork_ev);
   for (Buf& b : s.pool) release(b);
   if (s.comm) ncclCommDestroy(s.comm);
   if (s.stream) cudaStreamDestroy(s.stream);
@@ -1609,6 +1719,9 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
   } else if (k == "workspace_bytes") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
     c->opt_workspace_bytes = value;
+  } else if (k == "streams") {
+    if (value < 1 || value > 8) return fail(errp, ADEPT_CUDA_ERR_ARG, "streams must be in 1..8");
+    c->opt_streams = int(value);
   } else if (k == "smallg") {
     c->opt_smallg = value ? 1 : 0;
   } else if (k == "snap_rb") {

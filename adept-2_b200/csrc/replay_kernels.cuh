@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
                                                                int64_t n_stmts, double* __restrict__ g,
                                                                double* __restrict__ abuf, int64_t K, int64_t n_dirs,
                                                                uint8_t* __restrict__ rowact,
-                                                               uint8_t* __restrict__ aflag, int pitch, int ncb_live) {
+                                                               uint8_t* __restrict__ aflag, int pitch, int ncb_live,
+                                                               int cb_lo) {
   __shared__ int list[256];
   __shared__ int cnt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
     const int64_t t = t0 + threadIdx.x;
     if (t < total) {
       const int64_t k = t / ncb_live;
-      const int cb = static_cast<int>(t - k * ncb_live);
+      const int cb = cb_lo + static_cast<int>(t - k * ncb_live);
       const int64_t lhs = sched_lhs[j0 + k];
       if (rowact[lhs * pitch + cb]) list[atomicAdd(&cnt, 1)] = threadIdx.x;
       else aflag[k * pitch + cb] = 0;  // the row is all zero: a_s = 0, nothing to move
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
       if (q0 + u < n) {
         const int64_t t = t0 + list[q0 + u];
         kk[u] = t / ncb_live;
-        cbs[u] = static_cast<int>(t - kk[u] * ncb_live);
+        cbs[u] = cb_lo + static_cast<int>(t - kk[u] * ncb_live);
         ll[u] = sched_lhs[j0 + kk[u]];
         p[u] = g + ll[u] * K + (static_cast<int64_t>(cbs[u]) * 32 + lane) * V;  // rows are padded to K: in bounds
         a[u].load(p[u]);
@@ -347,7 +348,8 @@ struct TargetArgs {
   uint8_t* rowact;
   const uint8_t* aflag;
   int64_t K;
-  int n_colblocks;   // live column blocks of this pass
+  int n_colblocks;   // column blocks [cb_lo, n_colblocks) are handled by this launch
+  int cb_lo;
   int flag_pitch;    // row pitch of rowact/aflag
   int64_t n_dirs;
   int ref_block;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
   const int64_t n_recs = r1 - r0;
   const Rec* chunk = A.recs + r0;
   const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
-  const int cb0 = blockIdx.y * nwarps;
+  const int cb0 = A.cb_lo + blockIdx.y * nwarps;
   const int cb = cb0 + warp;
   const int ncb = A.flag_pitch;
   const bool live = cb < A.n_colblocks;
@@ -512,7 +514,8 @@ struct ForwardArgs {
   double* g;
   uint8_t* rowact;
   int64_t K;
-  int n_colblocks;
+  int n_colblocks;   // column blocks [cb_lo, n_colblocks) are handled by this launch
+  int cb_lo;
   int flag_pitch;
 };
 
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(256, 3) forward_level_kernel(ForwardArgs A) {
   const int64_t n_recs = r1 - r0;
   const Rec* chunk = A.recs + r0;
   const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
-  const int cb0 = blockIdx.y * nwarps;
+  const int cb0 = A.cb_lo + blockIdx.y * nwarps;
   const int cb = cb0 + warp;
   const int ncb = A.flag_pitch;
   const bool live = cb < A.n_colblocks;

@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--warps", type=int, default=8)
     ap.add_argument("--persistent", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=0)
     args = ap.parse_args()
     if args.workload in ("rosenbrock1e7", "ensemble1e5"):
         return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
@@ -317,6 +318,8 @@ def main():
     eng.set_option("warps_per_cta", args.warps)
     eng.set_option("persistent", args.persistent)
     eng.set_option("chunk_recs", args.chunk)
+    if args.streams:
+        eng.set_option("streams", args.streams)
 
     def barrier():
         torch.cuda.synchronize()

@@ -131,6 +131,9 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
      "workspace_bytes" cap for the direction-major gradient workspace (0 = 60% of free memory)
      "warps_per_cta" replay CTA size in warps (1..8, default 8)
      "window"        statements per dependency-analysis window (0 = default 65536)
+     "streams"       CUDA streams (1..8, default 4) over which independent direction ranges of a level-scheduled
+                     sweep are spread, each fed by its own host thread; hides the launch gap and tail of one
+                     range's step behind another range's kernels
      "smallg"        1 (default) = Jacobians of tapes whose gradient list fits shared memory (max_gradient*32*8 bytes
                      plus the reverse snapshot <= 200 KB) run in the shared-memory-resident kernel; 0 = never
      "chunk_recs"    records per level chunk = one CTA's share of a step (0 = default 64, max 256); takes effect at
