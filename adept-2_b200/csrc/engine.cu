@@ -719,7 +719,9 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     F.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
     F.flag_pitch = int(K / (32 * V));
     F.cb_lo = 0;
-    const int fwarps = std::max(1, std::min(plan.warps, F.n_colblocks));
+    int fwarps = std::max(1, std::min(plan.warps, F.n_colblocks));
+    if (F.n_colblocks >= 16 && F.n_colblocks / fwarps < c->opt_streams)
+      fwarps = std::max(1, std::min(fwarps, F.n_colblocks / std::max(1, c->opt_streams)));
     const bool sparse = !s.has_nonfinite;
     // independent direction ranges on separate streams, one issuing host thread each (see the reverse sweep)
     const int all_cb = F.n_colblocks;
@@ -796,7 +798,11 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     B.n_dirs = n_dirs;
     B.ref_block = c->opt_ref_block;
     B.cb_lo = 0;
-    const int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
+    // warps per CTA: with few column blocks (few directions on this GPU) use narrower CTAs so that there are still
+    // several independent direction ranges to spread over the streams
+    int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
+    if (!c->opt_persistent && B.n_colblocks >= 16 && B.n_colblocks / twarps < c->opt_streams)
+      twarps = std::max(1, std::min(twarps, B.n_colblocks / std::max(1, c->opt_streams)));
     const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
     if (c->opt_persistent && s.n_tchunks > 0) {
       // one cooperative kernel walks all steps (persistent_kernels.cuh)
