@@ -76,6 +76,7 @@ struct Shard {
   Buf level, fwd_l, fwd_chunk, foff, sched_lhs;   // level-major forward stream and its tables
   Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups
   Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
+  Buf sg_fwd_info, sg_rev_info;                    // per-step {items, records} ranges for the small-G kernel
   int32_t n_levels = 0;                            // number of steps
   int64_t n_chunks = 0, n_tchunks = 0, n_groups = 0, R_t = 0, max_step_width = 0;
   std::vector<int64_t> level_chunk;   // [n_levels+2] first forward chunk of each step
@@ -112,7 +113,6 @@ struct adept_cuda_ctx {
   int opt_time_kernels = 0;
   int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
   int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
-  int opt_snap_rb = 4;
   int opt_streams = 4;  // CUDA streams over which the direction ranges of a level-scheduled reverse sweep are spread
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   // stats
@@ -601,6 +601,16 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   CK(cudaMemcpyAsync(s.d_step_group.p, s.step_group.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_level_first.p, s.level_first.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_step_tchunk.p, s.step_tchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  RET(ensure(errp, s.sg_fwd_info, size_t(n_levels + 2) * 32));
+  RET(ensure(errp, s.sg_rev_info, size_t(n_levels + 2) * 32));
+  step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_level_first.as<int64_t>(), s.foff.as<int64_t>(),
+                                                                           n_levels, s.sg_fwd_info.as<longlong4>());
+  if (O > 0)
+    step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_step_group.as<int64_t>(), s.goff.as<int64_t>(),
+                                                                             n_levels, s.sg_rev_info.as<longlong4>());
+  else
+    CK(cudaMemsetAsync(s.sg_rev_info.p, 0, size_t(n_levels + 2) * 32, s.stream));
+  s.launches += 2;
   CK(cudaStreamSynchronize(s.stream));
   lap("an_target_ms");
   // 6. long statements (rare): listed for the single-direction forward sweep
@@ -919,8 +929,11 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
   s.stat["n_passes"] = 0;
   // tapes whose gradient list fits shared memory: one CTA per 32/64 directions walks all steps by itself
   if (D > 0 && c->opt_smallg && s.have_levels && c->opt_schedule != 1 && s.max_step_width < (int64_t(1) << 20)) {
-    const size_t kSmemCap = size_t(200) << 10;
-    auto need = [&](int dc) { return (size_t(s.max_gradient) + (mode == 1 ? size_t(s.max_step_width) : 0)) * size_t(dc) * 8; };
+    const size_t kSmemCap = size_t(220) << 10;
+    const size_t stage_bytes = ((sizeof(SgStage) + 15) / 16) * 16;
+    auto need = [&](int dc) {
+      return stage_bytes + (size_t(s.max_gradient) + (mode == 1 ? size_t(s.max_step_width) : 0)) * size_t(dc) * 8;
+    };
     int dc = 0;
     if (need(32) <= kSmemCap) dc = 32;
     if (need(64) <= kSmemCap && (D + 31) / 32 > 2 * s.sm_count) dc = 64;
@@ -933,6 +946,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       G.sched_lhs = s.sched_lhs.as<int32_t>();
       G.level_first = s.d_level_first.as<int64_t>();
       G.step_group = s.d_step_group.as<int64_t>();
+      G.step_info = (mode == 0 ? s.sg_fwd_info : s.sg_rev_info).as<longlong4>();
       G.n_levels = s.n_levels;
       G.max_gradient = s.max_gradient;
       G.seed_slot = seed_slots_dev;
@@ -1348,7 +1362,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -1730,8 +1744,6 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_streams = int(value);
   } else if (k == "smallg") {
     c->opt_smallg = value ? 1 : 0;
-  } else if (k == "snap_rb") {
-    c->opt_snap_rb = int(value);
   } else if (k == "chunk_recs") {
     if (value < 0 || value > 256) return fail(errp, ADEPT_CUDA_ERR_ARG, "chunk_recs must be in 0..256");
     c->opt_chunk_recs = value;

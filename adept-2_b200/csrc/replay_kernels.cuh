@@ -15,8 +15,11 @@
 // A CTA replays one "chunk" [chunk_begin[c], chunk_begin[c+1]) of the stream:
 //   * tape-ordered schedule: ONE chunk = the whole tape; the sweep is strictly sequential.
 //   * level schedule: the stream is permuted level-major by the device-side dependency
-//     analysis (analysis.cuh); the chunks of one level are launched together and are mutually
-//     independent (no two statements of a level touch a common slot).
+//     analysis (tape_kernels.cuh); the chunks of one step are launched together and are mutually
+//     independent (RAW/WAR/WAW between slot versions are respected by the step numbers).
+//     Level sweeps use forward_level_kernel / reverse_snapshot_kernel + reverse_target_kernel below
+//     (two directions per lane, block sparsity); the kernels in this first part replay a stream
+//     in tape order.
 //
 // Each warp keeps U gradient loads in flight ("batch").  Hazards inside a batch (a record
 // whose slot was written by an earlier record of the same batch) are resolved in registers by
@@ -64,9 +67,9 @@ __device__ __forceinline__ void issue_piece(StageRing& ring, const Rec* chunk, i
 }
 
 // ---------------------------------------------------------------------------------------
-// Forward sweep.  CHECK=true adds the in-batch forwarding test (needed whenever records of
-// a chunk may depend on each other: the tape-ordered schedule).  CHECK=false is for level
-// chunks, where no OP reads a slot that any TAIL of the same level writes.
+// Tape-ordered forward sweep.  CHECK=true adds the in-batch forwarding test (needed whenever
+// records of a chunk may depend on each other, i.e. always in tape order).  BATCH=true is the
+// ensemble mode of adept_cuda_jacobian_batch (per-member multipliers).
 // ---------------------------------------------------------------------------------------
 template <bool CHECK, bool BATCH>
 __global__ void __launch_bounds__(256, 3) replay_forward_kernel(ReplayArgs A) {

@@ -722,4 +722,14 @@ __global__ void target_step_tables_kernel(int64_t* __restrict__ step_group, int3
   step_tchunk[0] = 0;
 }
 
+// per-step table for the shared-memory-resident kernel: {first item, end item, first record, end record}
+__global__ void step_info_kernel(const int64_t* __restrict__ first, const int64_t* __restrict__ off, int32_t n_levels,
+                                 longlong4* __restrict__ info) {
+  const int64_t l = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (l > n_levels + 1) return;
+  if (l == 0 || l == n_levels + 1) { info[l] = make_longlong4(0, 0, 0, 0); return; }
+  const int64_t i0 = first[l], i1 = first[l + 1];
+  info[l] = make_longlong4(i0, i1, off[i0], off[i1]);
+}
+
 }  // namespace adept_b200
