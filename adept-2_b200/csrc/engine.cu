@@ -67,6 +67,7 @@ struct Shard {
   Buf stmt, mult, idx;
   int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
   bool have_tape = false;
+  bool have_tape_streams = false;
   bool has_nonfinite = false;  // some multiplier is inf/NaN: forward block-sparsity is then off
   // tape-order streams
   Buf fwd_t, rev_t, one_chunk;
@@ -255,12 +256,32 @@ int inclusive_sum(std::string* errp, Shard& s, Buf& tmp, const T* in, T* out, in
   return 0;
 }
 
+// Tape-order record streams (one chunk = the whole tape), built on first need: the tape-ordered kernels use
+// them; a tape that is replayed through its level schedule never pays for them (16 bytes x 2 per record).
+int ensure_tape_streams(Shard& s) {
+  std::string* errp = &s.err;
+  if (s.have_tape_streams) return 0;
+  const int64_t S = s.n_stmt - 1, O = s.n_ops, R = O + S;
+  if (R <= 0) { s.have_tape_streams = true; return 0; }
+  CK(cudaSetDevice(s.dev));
+  RET(ensure(errp, s.fwd_t, size_t(R) * sizeof(Rec)));
+  RET(ensure(errp, s.rev_t, size_t(R) * sizeof(Rec)));
+  build_streams_kernel<<<grid_for(std::max(O, S), 256, s.sm_count), 256, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), O, s.fwd_t.as<Rec>(),
+      s.rev_t.as<Rec>(), nullptr);
+  s.launches += 1;
+  CK(cudaGetLastError());
+  s.have_tape_streams = true;
+  return 0;
+}
+
 int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   std::string* errp = &s.err;
   CK(cudaSetDevice(s.dev));
   const int64_t S = s.n_stmt - 1, O = s.n_ops, R = O + S;
   s.R = R;
   s.have_levels = false;
+  s.have_tape_streams = false;
   s.n_levels = 0;
   s.n_chunks = 0;
   s.n_tchunks = 0;
@@ -290,15 +311,9 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   CK(cudaMemcpyAsync(s.one_chunk.p, one_chunk_host, sizeof one_chunk_host, cudaMemcpyHostToDevice, s.stream));
   CK(cudaStreamSynchronize(s.stream));  // one_chunk_host is a stack variable
   if (S == 0) return 0;
-  RET(ensure(errp, s.fwd_t, size_t(R) * sizeof(Rec)));
-  RET(ensure(errp, s.rev_t, size_t(R) * sizeof(Rec)));
-  build_streams_kernel<<<grid_for(std::max(O, S), T, s.sm_count), T, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), O, s.fwd_t.as<Rec>(),
-      s.rev_t.as<Rec>(), nullptr);
-  s.launches += 1;
-  CK(cudaGetLastError());
+  s.have_tape_streams = false;
   const bool want_levels = (c->opt_schedule != 1) && (S >= kMinLevelStatements || c->opt_schedule == 2);
-  if (!want_levels) return 0;
+  if (!want_levels) return ensure_tape_streams(s);
 
   // Temporaries live in a per-shard pool that survives the call (re-uploads of similar tapes then cost
   // no cudaMalloc/cudaFree, which dominated and jittered the analysis time); a pool above
@@ -710,6 +725,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
   const int threads = plan.warps * 32;
   const unsigned gy = unsigned((A.n_colblocks + plan.warps - 1) / plan.warps);
   if (!plan.use_levels) {
+    RET(ensure_tape_streams(s));
     A.recs = (mode == 0 ? s.fwd_t : s.rev_t).as<Rec>();
     A.chunk_begin = s.one_chunk.as<int64_t>();
     A.first_chunk = 0;
@@ -1282,6 +1298,7 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
   const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
   if (s.R > 0) {
     if (ordered) {
+      if (int rc = ensure_tape_streams(s)) { c->err = s.err; return rc; }
       ReplayArgs A{};
       A.g = g;
       A.K = 1;
@@ -1631,6 +1648,7 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
     // the shared structure replaces whatever tape this context held
     s.have_tape = false;
     s.have_levels = false;
+    s.have_tape_streams = false;
     RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
     RET(ensure(errp, s.idx, size_t(n_ops) * 4));
     RET(upload(s, s.stmt.p, statements, size_t(n_stmt) * 8));

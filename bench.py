@@ -54,6 +54,12 @@ WORKLOADS = {
     "synthetic1e7_fwd": dict(desc="BASELINE config 4 at 1/10 length: seeded random tape, 1e7 statements (mean 4 operands), "
                                   "2^20 slots, 8192x8192 Jacobian, forward sweeps", scheme="synthetic", n=10_000_000,
                              log2_slots=20, n_io=8192, mode=0),
+    "synthetic1e8_fwd": dict(desc="BASELINE config 4, full size: seeded random tape, 1e8 statements (mean 4 operands), "
+                                  "2^20 slots, 8192x8192 Jacobian, forward sweeps", scheme="synthetic", n=100_000_000,
+                             log2_slots=20, n_io=8192, mode=0),
+    "synthetic1e8_rev": dict(desc="BASELINE config 4, full size: seeded random tape, 1e8 statements (mean 4 operands), "
+                                  "2^20 slots, 8192x8192 Jacobian, reverse sweeps", scheme="synthetic", n=100_000_000,
+                             log2_slots=20, n_io=8192, mode=1),
     "synthetic1e7_rev": dict(desc="BASELINE config 4 at 1/10 length: seeded random tape, 1e7 statements (mean 4 operands), "
                                   "2^20 slots, 8192x8192 Jacobian, reverse sweeps", scheme="synthetic", n=10_000_000,
                              log2_slots=20, n_io=8192, mode=1),
