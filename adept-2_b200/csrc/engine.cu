@@ -31,15 +31,16 @@ using namespace adept_b200;
 
 namespace {
 
-constexpr int64_t kChunkRecs = 64;           // target records per level chunk (one CTA's share of a step); measured best of 16..256 on Toon nx=4096
-constexpr int64_t kLongThreshold = 1024;     // records; longer statements get cooperative kernels
-constexpr int64_t kMinLevelStatements = 4096;  // below this the tape-ordered kernel is used
-constexpr int64_t kDefaultWindow = 65536;       // statements per analysis window
-constexpr double kWideStepCtas = 4096.0;           // average CTAs per step above which one stream suffices
-constexpr int64_t kMaxStepWidth = int64_t(1) << 20;  // statements per step (wider steps are split)
-constexpr int64_t kHugeStatement = 65536;       // operands; a longer statement is an analysis window of its own
-constexpr size_t kStageBytes = size_t(32) << 20;
-constexpr size_t kPoolKeepBytes = size_t(8) << 30;  // analysis temporaries kept between uploads up to this size
+// Tuning constants (measured on B200)
+constexpr int64_t kChunkRecs = 64;                    // records per level chunk = one CTA's share of a step (best of 16..256 on Toon nx=4096)
+constexpr int64_t kLongThreshold = 1024;              // records; longer statements get cooperative kernels in single-direction sweeps
+constexpr int64_t kMinLevelStatements = 4096;         // shorter tapes are replayed in tape order (no schedule is built)
+constexpr int64_t kDefaultWindow = 65536;             // statements per dependency-analysis window
+constexpr int64_t kHugeStatement = 65536;             // operands; a longer statement is an analysis window of its own
+constexpr int64_t kMaxStepWidth = int64_t(1) << 20;   // statements per step (wider steps are split; bounds the reverse a-snapshot)
+constexpr double kWideStepCtas = 4096.0;              // average CTAs per step above which one CUDA stream suffices
+constexpr size_t kStageBytes = size_t(32) << 20;      // pinned staging buffer for pageable uploads (two of them)
+constexpr size_t kPoolKeepBytes = size_t(8) << 30;    // analysis temporaries kept between uploads up to this size
 
 struct Buf {
   void* p = nullptr;
