@@ -65,6 +65,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still draining; pdl_trigger() lets OUR successor do the same, pdl_wait() blocks until the predecessor
+// has completed and its writes are visible.  Everything before pdl_wait() must only touch data the
+// predecessor does not write (kernel arguments, the immutable record streams).  Both are no-ops for a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Rounded, never-contracted fp64 multiply-add: parity with the reference built without FMA
 // contraction ("multiply, round, add, round"; SURVEY.md section 7, oracle/replay_oracle.c).
 __device__ __forceinline__ double mul_add_rn(double acc, double m, double g) {

@@ -115,6 +115,7 @@ struct adept_cuda_ctx {
   int opt_time_kernels = 0;
   int opt_persistent = 0;  // 1: reverse level sweep as one cooperative kernel (measured slower than two launches per step)
   int64_t opt_chunk_recs = 0;  // records per level chunk (0 = kChunkRecs)
+  int opt_pdl = 1;      // programmatic dependent launch between the per-step kernels of a level sweep
   int opt_streams = 4;  // CUDA streams over which the direction ranges of a level-scheduled reverse sweep are spread
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   // stats
@@ -700,6 +701,23 @@ SweepPlan plan_sweep(const adept_cuda_ctx* c, const Shard& s, int64_t n_dirs) {
   return p;
 }
 
+// Launch with programmatic stream serialization (PDL, common.cuh): the kernel may begin while its predecessor
+// in the stream drains; it calls pdl_wait() before touching anything the predecessor writes.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // next event of the per-launch timing pool, recorded on the shard's stream
 int mark(Shard& s) {
   std::string* errp = &s.err;
@@ -770,6 +788,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     }
     std::vector<int> rcs(nstr, 0);
     std::vector<double> nl(nstr, 0.0);
+    const bool pdl = c->opt_pdl && !c->opt_time_kernels;
     auto run_stream = [&](int i) {
       if (cudaSetDevice(s.dev) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
       const int g_lo = int(int64_t(groups) * i / nstr), g_hi = int(int64_t(groups) * (i + 1) / nstr);
@@ -784,8 +803,8 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         Fi.first_chunk = c0;
         const dim3 grid(unsigned(c1 - c0), unsigned(g_hi - g_lo));
         if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-        if (sparse) forward_level_kernel<V, true><<<grid, fwarps * 32, 0, st>>>(Fi);
-        else forward_level_kernel<V, false><<<grid, fwarps * 32, 0, st>>>(Fi);
+        if (sparse) launch_pdl(forward_level_kernel<V, true>, grid, dim3(fwarps * 32), st, pdl, Fi);
+        else launch_pdl(forward_level_kernel<V, false>, grid, dim3(fwarps * 32), st, pdl, Fi);
         if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         nl[i] += 1;
       }
@@ -879,6 +898,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const int groups = (all_cb + twarps - 1) / twarps;
     std::vector<int> rcs(nstr, 0);
     std::vector<double> nl(nstr, 0.0);
+    const bool pdl = c->opt_pdl && !c->opt_time_kernels;
     auto run_stream = [&](int i) {
       if (cudaSetDevice(s.dev) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
       const int g_lo = int(int64_t(groups) * i / nstr), g_hi = int(int64_t(groups) * (i + 1) / nstr);
@@ -893,14 +913,14 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
         if (n <= 0) continue;
         const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
-        reverse_snapshot_kernel<V, 4><<<unsigned((n * ncols + 255) / 256), 256, 0, st>>>(
-            s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
-            s.aflag.as<uint8_t>(), B.flag_pitch, ncols, cb_lo);
+        launch_pdl(reverse_snapshot_kernel<V, 4>, dim3(unsigned((n * ncols + 255) / 256)), dim3(256), st, pdl,
+                   s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
+                   s.aflag.as<uint8_t>(), B.flag_pitch, ncols, cb_lo);
         nl[i] += 1;
         if (c1 > c0) {
           Bi.first_chunk = c0;
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-          reverse_target_kernel<V><<<dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), twarps * 32, 0, st>>>(Bi);
+          launch_pdl(reverse_target_kernel<V>, dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), dim3(twarps * 32), st, pdl, Bi);
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           nl[i] += 1;
         }
@@ -1758,6 +1778,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
   } else if (k == "workspace_bytes") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "workspace_bytes must be >= 0");
     c->opt_workspace_bytes = value;
+  } else if (k == "pdl") {
+    c->opt_pdl = value ? 1 : 0;
   } else if (k == "streams") {
     if (value < 1 || value > 8) return fail(errp, ADEPT_CUDA_ERR_ARG, "streams must be in 1..8");
     c->opt_streams = int(value);

@@ -286,10 +286,12 @@ __global__ void __launch_bounds__(256) reverse_snapshot_kernel(const int32_t* __
   __shared__ int list[256];
   __shared__ int cnt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
   const int64_t total = n_stmts * ncb_live;
+  pdl_wait();   // the previous step's target kernel wrote the rows and activity bytes read below
   {
     const int64_t t = t0 + threadIdx.x;
     if (t < total) {
@@ -394,8 +396,10 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_trigger();
   if (threadIdx.x == 0)
     for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
+  pdl_wait();   // records (immutable) are already in flight; rows, snapshot and activity bytes come from the previous kernel
 
   LaneVec<V> acc;
   acc.zero();
@@ -545,8 +549,10 @@ __global__ void __launch_bounds__(256, 3) forward_level_kernel(ForwardArgs A) {
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_trigger();
   if (threadIdx.x == 0)
     for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
+  pdl_wait();   // records (immutable) are already in flight; gradient rows come from the previous step
 
   LaneVec<V> acc;
   acc.zero();

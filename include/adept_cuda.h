@@ -134,6 +134,8 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
      "streams"       CUDA streams (1..8, default 4) over which independent direction ranges of a level-scheduled
                      sweep are spread, each fed by its own host thread; hides the launch gap and tail of one
                      range's step behind another range's kernels
+     "pdl"           1 (default) = the per-step kernels of a level sweep are chained with programmatic dependent
+                     launch: a step's kernel starts (and TMA-fetches its records) while the previous one drains
      "smallg"        1 (default) = Jacobians of tapes whose gradient list fits shared memory (max_gradient*32*8 bytes
                      plus the reverse snapshot <= 200 KB) run in the shared-memory-resident kernel; 0 = never
      "chunk_recs"    records per level chunk = one CTA's share of a step (0 = default 64, max 256); takes effect at
