@@ -34,6 +34,8 @@ SIGNATURES = {
     "adept_cuda_jacobian_device": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _vp, _i64, _i64]),
     "adept_cuda_tangent_linear": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "adept_cuda_adjoint": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "adept_cuda_tangent_linear_device": (C.c_int, [_vp, _vp, C.c_int]),
+    "adept_cuda_adjoint_device": (C.c_int, [_vp, _vp, C.c_int]),
     "adept_cuda_jacobian_batch": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64,
                                             _vp, _i64, _vp, _i64, _vp]),
     "adept_cuda_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),

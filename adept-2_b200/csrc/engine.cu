@@ -1315,7 +1315,7 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
 
 
 // single-direction sweep on shard 0: gradient vector in/out on the host
-int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initialized, int flags) {
+int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initialized, int flags, bool on_device = false) {
   if (!c) return ADEPT_CUDA_ERR_ARG;
   std::string* errp = &c->err;
   Shard& s = c->sh[0];
@@ -1324,9 +1324,12 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
   if (!gradient_host) return fail(errp, ADEPT_CUDA_ERR_ARG, "null gradient vector");
   CK(cudaSetDevice(s.dev));
   const int64_t G = s.max_gradient;
-  RET(ensure(errp, s.g1, size_t(G) * 8));
-  double* g = s.g1.as<double>();
-  if (int rc = upload(s, g, gradient_host, size_t(G) * 8)) { c->err = s.err; return rc; }
+  double* g = gradient_host;   // device-resident gradient vector: swept in place
+  if (!on_device) {
+    RET(ensure(errp, s.g1, size_t(G) * 8));
+    g = s.g1.as<double>();
+    if (int rc = upload(s, g, gradient_host, size_t(G) * 8)) { c->err = s.err; return rc; }
+  }
   CK(cudaEventRecord(s.ev[0], s.stream));
   const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
   if (s.R > 0) {
@@ -1382,7 +1385,7 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
   }
   CK(cudaEventRecord(s.ev[1], s.stream));
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(gradient_host, g, size_t(G) * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (!on_device) CK(cudaMemcpyAsync(gradient_host, g, size_t(G) * 8, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
@@ -1645,6 +1648,14 @@ int adept_cuda_tangent_linear(adept_cuda_ctx* c, double* gradient_host, int init
 
 int adept_cuda_adjoint(adept_cuda_ctx* c, double* gradient_host, int initialized, int flags) {
   return do_sweep1(c, 1, gradient_host, initialized, flags);
+}
+
+int adept_cuda_tangent_linear_device(adept_cuda_ctx* c, double* gradient_device, int flags) {
+  return do_sweep1(c, 0, gradient_device, 1, flags, true);
+}
+
+int adept_cuda_adjoint_device(adept_cuda_ctx* c, double* gradient_device, int flags) {
+  return do_sweep1(c, 1, gradient_device, 1, flags, true);
 }
 
 int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statements, int64_t n_stmt,

@@ -161,6 +161,14 @@ class Engine:
         self._chk(self.L.adept_cuda_adjoint(self.h, _ptr(g), int(bool(initialized)), int(flags)))
         return g
 
+    def adjoint_device(self, gradient_ptr: int, flags=0):
+        """In-place reverse sweep of a device-resident gradient vector (raw device pointer on devices[0])."""
+        self._chk(self.L.adept_cuda_adjoint_device(self.h, C.c_void_p(gradient_ptr), int(flags)))
+
+    def tangent_linear_device(self, gradient_ptr: int, flags=0):
+        """In-place forward sweep of a device-resident gradient vector."""
+        self._chk(self.L.adept_cuda_tangent_linear_device(self.h, C.c_void_p(gradient_ptr), int(flags)))
+
     def jacobian_batch(self, mode, stmt, idx, max_gradient, multipliers, indep, dep):
         """multipliers: float64 [n_ops, n_members].  Returns [n_members, n_indep, n_dep] (each member
         column-major n_dep x n_indep, the reference's default layout)."""

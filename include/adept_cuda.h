@@ -108,6 +108,13 @@ int  adept_cuda_jacobian_device(adept_cuda_ctx* ctx, int mode,
 int  adept_cuda_tangent_linear(adept_cuda_ctx* ctx, double* gradient_host, int initialized, int flags);
 int  adept_cuda_adjoint(adept_cuda_ctx* ctx, double* gradient_host, int initialized, int flags);
 
+/* The same sweeps IN PLACE on a gradient vector that already lives on devices[0] (max_gradient doubles): no
+   host<->device copies.  For optimiser loops that keep the gradient on the GPU between iterations (the callers of
+   BASELINE config 5: adept/minimize_limited_memory_bfgs.cpp:115-139, adept/line_search.cpp:45) and for
+   checkpoint-chained replay (test/test_checkpoint.cpp:209-225).  Synchronous: the sweep has finished on return. */
+int  adept_cuda_tangent_linear_device(adept_cuda_ctx* ctx, double* gradient_device, int flags);
+int  adept_cuda_adjoint_device(adept_cuda_ctx* ctx, double* gradient_device, int flags);
+
 /* Ensemble of B tapes sharing ONE structure (statements, index, indep, dep) with per-member
    multipliers laid out [op][member] (BASELINE config 3: simulate_radiances ensemble).  Output is
    member-major: jac_out[b*n_dep*n_indep + i + j*n_dep] (the reference's default column-major

@@ -321,3 +321,23 @@ def test_ensemble_jacobians(engine, po, pkg, B):
             rc, want = po.jacobian(r["stmt"], np.ascontiguousarray(mm[:, b]), r["idx"], r["max_gradient"], r["indep"],
                                    r["dep"], mode)
             assert rc == 0 and same_bits(got[b], want), (mode, b)
+
+
+def test_device_resident_sweeps(engine, po, pkg):
+    """adept_cuda_adjoint_device / _tangent_linear_device: in-place sweeps of a gradient vector that stays on the
+    GPU (optimiser loops, checkpoint chains): same bits as the host-vector entry points and the oracle."""
+    import torch
+    t = pkg.tapegen.rosenbrock_tape(5000)
+    for schedule in (ORDERED, LEVELS):
+        upload(engine, t, schedule)
+        flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
+        g0 = np.zeros(t["max_gradient"]); g0[t["dep"][0]] = 1.0
+        d = torch.from_numpy(g0).cuda()
+        engine.adjoint_device(d.data_ptr(), flags)
+        assert same_bits(d.cpu().numpy(), po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
+        x = np.zeros(t["max_gradient"]); x[t["indep"]] = np.linspace(-1, 1, t["indep"].size)
+        d = torch.from_numpy(x).cuda()
+        engine.tangent_linear_device(d.data_ptr(), flags)
+        engine.tangent_linear_device(d.data_ptr(), flags)      # twice on the same vector, as test_derivatives.cpp:25-29 does
+        want = po.tangent_linear(t["stmt"], t["mult"], t["idx"], po.tangent_linear(t["stmt"], t["mult"], t["idx"], x))
+        assert same_bits(d.cpu().numpy(), want)
