@@ -482,6 +482,14 @@ def main():
                 "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
                         "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}
 
+    if roof is not None:
+        try:   # DRAM traffic of one profiled launch (ncu --set full), when a capture for this workload is on file
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            if tr:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_sample"] = tr["launch"]
+        except Exception:
+            pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
