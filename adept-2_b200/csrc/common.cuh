@@ -24,7 +24,11 @@ struct __align__(16) Rec {
 };
 static_assert(sizeof(Rec) == 16, "Rec must be 16 bytes (TMA bulk-copy granule)");
 
-enum : int32_t { REC_OP = 0, REC_MARK = 1 /* TAIL in a forward stream, HEAD in a reverse stream */ };
+enum : int32_t {
+  REC_OP = 0,
+  REC_MARK = 1,  // TAIL in a forward stream, HEAD in a reverse stream
+  REC_ZMARK = 2  // fused reverse stream only: a HEAD whose sum starts from +0.0 (the target is an LHS of the step)
+};
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP) -- 1-D global -> shared.

@@ -41,6 +41,7 @@ constexpr int64_t kMaxStepWidth = int64_t(1) << 20;   // statements per step (wi
 constexpr double kWideStepCtas = 4096.0;              // average CTAs per step above which one CUDA stream suffices
 constexpr size_t kStageBytes = size_t(32) << 20;      // pinned staging buffer for pageable uploads (two of them)
 constexpr size_t kPoolKeepBytes = size_t(8) << 30;    // analysis temporaries kept between uploads up to this size
+constexpr size_t kPoolSlots = 48;                     // analysis temporaries (Shard::pool)
 
 struct Buf {
   void* p = nullptr;
@@ -76,7 +77,14 @@ struct Shard {
   // level schedule
   bool have_levels = false;
   Buf level, fwd_l, fwd_chunk, foff, sched_lhs;   // level-major forward stream and its tables
-  Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups
+  Buf tgt, tchunk, goff;                           // reverse target stream, its chunks and groups (built on first need)
+  Buf pos_in_sched;                                // schedule position of every statement (input of the target stream)
+  bool have_target = false;
+  // fused reverse stream (versioned rows, one kernel per step; built on first need)
+  bool have_fused = false;
+  Buf ftgt, fchunk, fpar, out_rows;
+  int64_t n_fchunks = 0, R_f = 0, chunk_recs = 0;
+  std::vector<int64_t> step_fchunk;   // [n_levels+2] first fused chunk of each step
   Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
   Buf sg_fwd_info, sg_rev_info;                    // per-step {items, records} ranges for the small-G kernel
   int32_t n_levels = 0;                            // number of steps
@@ -118,6 +126,7 @@ struct adept_cuda_ctx {
   int opt_pdl = 1;      // programmatic dependent launch between the per-step kernels of a level sweep
   int opt_streams = 4;  // CUDA streams over which the direction ranges of a level-scheduled reverse sweep are spread
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
+  int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -289,6 +298,17 @@ int ensure_tape_streams(Shard& s) {
   return 0;
 }
 
+// Releases an oversized pool of analysis temporaries when a builder returns.
+struct PoolGuard {
+  Shard& s;
+  ~PoolGuard() {
+    size_t total = 0;
+    for (Buf& b : s.pool) total += b.bytes;
+    if (total > kPoolKeepBytes)
+      for (Buf& b : s.pool) release(b);
+  }
+};
+
 int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   std::string* errp = &s.err;
   CK(cudaSetDevice(s.dev));
@@ -296,9 +316,12 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   s.R = R;
   s.have_levels = false;
   s.have_tape_streams = false;
+  s.have_target = false;
+  s.have_fused = false;
   s.n_levels = 0;
   s.n_chunks = 0;
   s.n_tchunks = 0;
+  s.n_fchunks = 0;
   s.n_groups = 0;
   s.max_step_width = 0;
   s.long_stmts.clear();
@@ -332,21 +355,12 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   // Temporaries live in a per-shard pool that survives the call (re-uploads of similar tapes then cost
   // no cudaMalloc/cudaFree, which dominated and jittered the analysis time); a pool above
   // kPoolKeepBytes is released on exit.
-  struct PoolGuard {
-    Shard& s;
-    ~PoolGuard() {
-      size_t total = 0;
-      for (Buf& b : s.pool) total += b.bytes;
-      if (total > kPoolKeepBytes)
-        for (Buf& b : s.pool) release(b);
-    }
-  } pool_guard{s};
-  s.pool.resize(34);
+  PoolGuard pool_guard{s};
+  s.pool.resize(kPoolSlots);
   Buf &cap = s.pool[0], &tab_off = s.pool[1], &tables = s.pool[2], &wdepth = s.pool[3], &wbase = s.pool[4],
       &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &nrec = s.pool[10],
-      &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &pos_in_sched = s.pool[15],
-      &incl = s.pool[16], &gstep = s.pool[17], &cflag = s.pool[18], &cincl = s.pool[19], &sgroup = s.pool[20],
-      &stchunk = s.pool[21], &lo = s.pool[22], &lc = s.pool[23];
+      &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &lo = s.pool[22], &lc = s.pool[23];
+  Buf& pos_in_sched = s.pos_in_sched;
 
   auto tp = std::chrono::steady_clock::now();
   auto lap = [&](const char* key) {
@@ -477,6 +491,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   // one CTA's share of a step: 64 records when steps are narrow (shorter critical path per launch), 128 when they
   // are wide (measured: Toon nx=4096 171 vs 196 ms; synthetic forward 537 vs 462 ms)
   const int64_t chunk_recs = c->opt_chunk_recs > 0 ? c->opt_chunk_recs : (R / std::max(1, n_levels) >= 32768 ? 2 * kChunkRecs : kChunkRecs);
+  s.chunk_recs = chunk_recs;
   // 4. statements sorted by step (stable), record offsets, chunk table, level-major forward stream
   const int64_t nmax = std::max(S, O);
   RET(ensure(errp, k0, size_t(nmax) * 4));
@@ -565,83 +580,15 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     s.max_step_width = std::max(s.max_step_width, s.level_first[l + 1] - s.level_first[l]);
 
   lap("an_forward_ms");
-  // 5. reverse target stream: operations sorted by (step, slot, reference reverse order)
-  s.step_group.assign(size_t(n_levels) + 2, 0);
-  s.step_tchunk.assign(size_t(n_levels) + 2, 0);
-  if (O > 0) {
-    target_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt,
-                                                                       s.idx.as<int32_t>(), O, k0.as<uint32_t>(),
-                                                                       v0.as<uint32_t>());
-    s.launches += 1;
-    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(s.max_gradient)));
-    target_step_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
-        s.stmt.as<int2>(), s.n_stmt, v0.as<uint32_t>(), O, s.level.as<int32_t>(), k0.as<uint32_t>());
-    s.launches += 1;
-    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(int64_t(n_levels) + 1)));
-    target_flags_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), v0.as<uint32_t>(),
-                                                                        s.idx.as<int32_t>(), O, flag.as<int32_t>());
-    s.launches += 1;
-    RET(ensure(errp, incl, size_t(O) * 4));
-    RET(inclusive_sum(errp, s, tmp, flag.as<int32_t>(), incl.as<int32_t>(), O));
-    int32_t n_groups32 = 0;
-    CK(cudaMemcpyAsync(&n_groups32, incl.as<int32_t>() + (O - 1), 4, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    const int64_t n_groups = n_groups32;
-    const int64_t R_t = O + n_groups;
-    s.n_groups = n_groups;
-    s.R_t = R_t;
-    RET(ensure(errp, s.tgt, size_t(R_t) * sizeof(Rec)));
-    RET(ensure(errp, s.goff, size_t(n_groups + 1) * 8));
-    RET(ensure(errp, gstep, size_t(n_groups + 1) * 4));
-    target_emit_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
-        s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), k0.as<uint32_t>(), v0.as<uint32_t>(),
-        flag.as<int32_t>(), incl.as<int32_t>(), O, pos_in_sched.as<int32_t>(), lfirst.as<int64_t>(),
-        s.tgt.as<Rec>(), s.goff.as<int64_t>(), gstep.as<int32_t>());
-    s.launches += 1;
-    CK(cudaMemcpyAsync(s.goff.as<int64_t>() + n_groups, &s.R_t, 8, cudaMemcpyHostToDevice, s.stream));
-    RET(ensure(errp, cflag, size_t(n_groups + 1) * 4));
-    RET(ensure(errp, cincl, size_t(n_groups + 1) * 4));
-    RET(ensure(errp, sgroup, size_t(n_levels + 2) * 8));
-    RET(ensure(errp, stchunk, size_t(n_levels + 2) * 8));
-    CK(cudaMemsetAsync(sgroup.p, 0xFF, size_t(n_levels + 2) * 8, s.stream));
-    target_chunk_flags_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(
-        s.goff.as<int64_t>(), gstep.as<int32_t>(), n_groups, chunk_recs, cflag.as<int32_t>(), sgroup.as<int64_t>());
-    s.launches += 1;
-    RET(inclusive_sum(errp, s, tmp, cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups));
-    int32_t n_tchunks32 = 0;
-    CK(cudaMemcpyAsync(&n_tchunks32, cincl.as<int32_t>() + (n_groups - 1), 4, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-    s.n_tchunks = n_tchunks32;
-    RET(ensure(errp, s.tchunk, size_t(s.n_tchunks + 1) * 8));
-    target_chunk_table_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(
-        s.goff.as<int64_t>(), cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups, s.n_tchunks, R_t,
-        s.tchunk.as<int64_t>());
-    target_step_tables_kernel<<<1, 1, 0, s.stream>>>(sgroup.as<int64_t>(), n_levels, n_groups, cincl.as<int32_t>(),
-                                                     s.n_tchunks, stchunk.as<int64_t>());
-    s.launches += 2;
-    CK(cudaMemcpyAsync(s.step_group.data(), sgroup.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaMemcpyAsync(s.step_tchunk.data(), stchunk.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
-  }
-
+  // 5. the reverse streams (two-kernel target stream, fused stream) are built on first need:
+  //    ensure_target_stream / ensure_fused_stream
   RET(ensure(errp, s.d_level_first, size_t(n_levels + 2) * 8));
-  RET(ensure(errp, s.d_step_tchunk, size_t(n_levels + 2) * 8));
-  RET(ensure(errp, s.d_step_group, size_t(n_levels + 2) * 8));
-  CK(cudaMemcpyAsync(s.d_step_group.p, s.step_group.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   CK(cudaMemcpyAsync(s.d_level_first.p, s.level_first.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
-  CK(cudaMemcpyAsync(s.d_step_tchunk.p, s.step_tchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
   RET(ensure(errp, s.sg_fwd_info, size_t(n_levels + 2) * 32));
-  RET(ensure(errp, s.sg_rev_info, size_t(n_levels + 2) * 32));
   step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_level_first.as<int64_t>(), s.foff.as<int64_t>(),
                                                                            n_levels, s.sg_fwd_info.as<longlong4>());
-  if (O > 0)
-    step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_step_group.as<int64_t>(), s.goff.as<int64_t>(),
-                                                                             n_levels, s.sg_rev_info.as<longlong4>());
-  else
-    CK(cudaMemsetAsync(s.sg_rev_info.p, 0, size_t(n_levels + 2) * 32, s.stream));
-  s.launches += 2;
+  s.launches += 1;
   CK(cudaStreamSynchronize(s.stream));
-  lap("an_target_ms");
   // 6. long statements (rare): listed for the single-direction forward sweep
   {
     const int max_long = 4096;
@@ -679,6 +626,200 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   return 0;
 }
 
+
+
+// chunk and step tables of a reverse stream made of target groups (shared by the two-kernel target stream and
+// the fused stream): goff[g] = record offset of group g (goff[n_groups] = n_recs), gstep[g] = its step.
+int build_group_tables(Shard& s, int64_t n_groups, int64_t n_recs, const int64_t* goff, const int32_t* gstep, Buf& chunk_tab,
+                       int64_t* n_chunks_out, std::vector<int64_t>& step_group_h, std::vector<int64_t>& step_chunk_h,
+                       Buf* d_step_group) {
+  std::string* errp = &s.err;
+  const int T = 256;
+  const int32_t n_levels = s.n_levels;
+  Buf &tmp = s.pool[9], &cflag = s.pool[18], &cincl = s.pool[19], &sgroup = s.pool[20], &stchunk = s.pool[21];
+  RET(ensure(errp, cflag, size_t(n_groups + 1) * 4));
+  RET(ensure(errp, cincl, size_t(n_groups + 1) * 4));
+  RET(ensure(errp, sgroup, size_t(n_levels + 2) * 8));
+  RET(ensure(errp, stchunk, size_t(n_levels + 2) * 8));
+  CK(cudaMemsetAsync(sgroup.p, 0xFF, size_t(n_levels + 2) * 8, s.stream));
+  target_chunk_flags_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(goff, gstep, n_groups, s.chunk_recs,
+                                                                                  cflag.as<int32_t>(), sgroup.as<int64_t>());
+  s.launches += 1;
+  RET(inclusive_sum(errp, s, tmp, cflag.as<int32_t>(), cincl.as<int32_t>(), n_groups));
+  int32_t n_chunks32 = 0;
+  CK(cudaMemcpyAsync(&n_chunks32, cincl.as<int32_t>() + (n_groups - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  const int64_t n_chunks = n_chunks32;
+  *n_chunks_out = n_chunks;
+  RET(ensure(errp, chunk_tab, size_t(n_chunks + 1) * 8));
+  target_chunk_table_kernel<<<grid_for(n_groups, T, s.sm_count), T, 0, s.stream>>>(goff, cflag.as<int32_t>(), cincl.as<int32_t>(),
+                                                                                  n_groups, n_chunks, n_recs,
+                                                                                  chunk_tab.as<int64_t>());
+  target_step_tables_kernel<<<1, 1, 0, s.stream>>>(sgroup.as<int64_t>(), n_levels, n_groups, cincl.as<int32_t>(), n_chunks,
+                                                   stchunk.as<int64_t>());
+  s.launches += 2;
+  step_group_h.assign(size_t(n_levels) + 2, 0);
+  step_chunk_h.assign(size_t(n_levels) + 2, 0);
+  CK(cudaMemcpyAsync(step_group_h.data(), sgroup.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(step_chunk_h.data(), stchunk.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (d_step_group) {
+    RET(ensure(errp, *d_step_group, size_t(n_levels + 2) * 8));
+    CK(cudaMemcpyAsync(d_step_group->p, sgroup.p, size_t(n_levels + 2) * 8, cudaMemcpyDeviceToDevice, s.stream));
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+// Reverse target stream of the two-kernel level sweep (snapshot + gather), the shared-memory kernel, the persistent
+// kernel and the single-direction adjoint: operations sorted by (step, slot, reference reverse order).  Built on
+// first need: a tape that is only swept forward, or backward through the fused stream, never pays for it.
+int ensure_target_stream(const adept_cuda_ctx* c, Shard& s) {
+  std::string* errp = &s.err;
+  if (s.have_target) return 0;
+  if (!s.have_levels) return fail(errp, ADEPT_CUDA_ERR_ARG, "no level schedule: no target stream");
+  CK(cudaSetDevice(s.dev));
+  const int T = 256;
+  const int64_t O = s.n_ops;
+  const int32_t n_levels = s.n_levels;
+  auto t0 = std::chrono::steady_clock::now();
+  PoolGuard pool_guard{s};
+  s.pool.resize(kPoolSlots);
+  Buf &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &flag = s.pool[12],
+      &incl = s.pool[16], &gstep = s.pool[17];
+  s.step_group.assign(size_t(n_levels) + 2, 0);
+  s.step_tchunk.assign(size_t(n_levels) + 2, 0);
+  s.n_groups = 0;
+  s.n_tchunks = 0;
+  s.R_t = 0;
+  RET(ensure(errp, s.d_step_tchunk, size_t(n_levels + 2) * 8));
+  RET(ensure(errp, s.d_step_group, size_t(n_levels + 2) * 8));
+  RET(ensure(errp, s.sg_rev_info, size_t(n_levels + 2) * 32));
+  if (O > 0) {
+    for (Buf* b : {&k0, &k1, &v0, &v1}) RET(ensure(errp, *b, size_t(O) * 4));
+    RET(ensure(errp, flag, size_t(O + 1) * 4));
+    target_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt,
+                                                                       s.idx.as<int32_t>(), O, k0.as<uint32_t>(),
+                                                                       v0.as<uint32_t>());
+    s.launches += 1;
+    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(s.max_gradient)));
+    target_step_keys_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
+        s.stmt.as<int2>(), s.n_stmt, v0.as<uint32_t>(), O, s.level.as<int32_t>(), k0.as<uint32_t>());
+    s.launches += 1;
+    RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, O, bits_for(int64_t(n_levels) + 1)));
+    target_flags_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), v0.as<uint32_t>(),
+                                                                        s.idx.as<int32_t>(), O, flag.as<int32_t>());
+    s.launches += 1;
+    RET(ensure(errp, incl, size_t(O) * 4));
+    RET(inclusive_sum(errp, s, tmp, flag.as<int32_t>(), incl.as<int32_t>(), O));
+    int32_t n_groups32 = 0;
+    CK(cudaMemcpyAsync(&n_groups32, incl.as<int32_t>() + (O - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    const int64_t n_groups = n_groups32;
+    const int64_t R_t = O + n_groups;
+    s.n_groups = n_groups;
+    s.R_t = R_t;
+    RET(ensure(errp, s.tgt, size_t(R_t) * sizeof(Rec)));
+    RET(ensure(errp, s.goff, size_t(n_groups + 1) * 8));
+    RET(ensure(errp, gstep, size_t(n_groups + 1) * 4));
+    target_emit_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(
+        s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), k0.as<uint32_t>(), v0.as<uint32_t>(),
+        flag.as<int32_t>(), incl.as<int32_t>(), O, s.pos_in_sched.as<int32_t>(), s.d_level_first.as<int64_t>(),
+        s.tgt.as<Rec>(), s.goff.as<int64_t>(), gstep.as<int32_t>());
+    s.launches += 1;
+    CK(cudaMemcpyAsync(s.goff.as<int64_t>() + n_groups, &s.R_t, 8, cudaMemcpyHostToDevice, s.stream));
+    RET(build_group_tables(s, n_groups, R_t, s.goff.as<int64_t>(), gstep.as<int32_t>(), s.tchunk, &s.n_tchunks, s.step_group,
+                           s.step_tchunk, nullptr));
+  }
+  CK(cudaMemcpyAsync(s.d_step_group.p, s.step_group.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemcpyAsync(s.d_step_tchunk.p, s.step_tchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  if (O > 0)
+    step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_step_group.as<int64_t>(), s.goff.as<int64_t>(),
+                                                                             n_levels, s.sg_rev_info.as<longlong4>());
+  else
+    CK(cudaMemsetAsync(s.sg_rev_info.p, 0, size_t(n_levels + 2) * 32, s.stream));
+  s.launches += 1;
+  CK(cudaStreamSynchronize(s.stream));
+  CK(cudaGetLastError());
+  s.stat["an_target_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  s.have_target = true;
+  return 0;
+}
+
+// Fused reverse stream over versioned rows (tape_kernels.cuh, "FUSED reverse stream"; the sequential statement of
+// the construction is tests/test_fused_stream_model.py).  Built on first need.
+int ensure_fused_stream(const adept_cuda_ctx* c, Shard& s) {
+  std::string* errp = &s.err;
+  if (s.have_fused) return 0;
+  if (!s.have_levels) return fail(errp, ADEPT_CUDA_ERR_ARG, "no level schedule: no fused stream");
+  CK(cudaSetDevice(s.dev));
+  const int T = 256;
+  const int64_t S = s.n_stmt - 1, O = s.n_ops, n = O + S, G = s.max_gradient;
+  const int32_t n_levels = s.n_levels;
+  auto t0 = std::chrono::steady_clock::now();
+  PoolGuard pool_guard{s};
+  s.pool.resize(kPoolSlots);
+  Buf &k0 = s.pool[5], &k1 = s.pool[6], &v0 = s.pool[7], &v1 = s.pool[8], &tmp = s.pool[9], &flag = s.pool[12],
+      &gincl = s.pool[16], &gstep = s.pool[17], &isl = s.pool[34], &E = s.pool[35], &e0 = s.pool[36], &par = s.pool[37],
+      &hflag = s.pool[38], &hincl = s.pool[39], &goff = s.pool[40];
+  for (Buf* b : {&k0, &k1, &v0, &v1, &isl, &E, &hflag, &hincl, &gincl}) RET(ensure(errp, *b, size_t(n) * 4));
+  RET(ensure(errp, flag, size_t(n + 1) * 4));
+  RET(ensure(errp, e0, size_t(G) * 4));
+  RET(ensure(errp, par, size_t(n)));
+  RET(ensure(errp, s.fpar, size_t(G)));
+  // references in sweep order, sorted by slot: writers already passed -> row parities
+  fused_keys_kernel<<<grid_for(std::max(O, S), T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(),
+                                                                                 O, k0.as<uint32_t>(), v0.as<uint32_t>());
+  s.launches += 1;
+  RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, n, bits_for(G)));
+  fused_islhs_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(v0.as<uint32_t>(), n, O, isl.as<int32_t>());
+  s.launches += 1;
+  RET(exclusive_sum(errp, s, tmp, isl.as<int32_t>(), E.as<int32_t>(), n));
+  CK(cudaMemsetAsync(s.fpar.p, 0, size_t(G), s.stream));
+  fused_segstart_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), E.as<int32_t>(), n, e0.as<int32_t>());
+  fused_parity_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(k0.as<uint32_t>(), v0.as<uint32_t>(), isl.as<int32_t>(),
+                                                                      E.as<int32_t>(), e0.as<int32_t>(), n, par.as<uint8_t>(),
+                                                                      s.fpar.as<uint8_t>());
+  s.launches += 2;
+  // sorted by (step, slot, sweep order): groups, inserted heads, emission
+  fused_step_keys_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, O, v0.as<uint32_t>(), n,
+                                                                         s.level.as<int32_t>(), k0.as<uint32_t>());
+  s.launches += 1;
+  RET(sort_pairs(errp, s, k0, k1, v0, v1, tmp, n, bits_for(int64_t(n_levels) + 1)));
+  RET(ensure(errp, s.scratch, 64));
+  CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
+  fused_flags_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.idx.as<int32_t>(), O, k0.as<uint32_t>(),
+                                                                     v0.as<uint32_t>(), n, flag.as<int32_t>(),
+                                                                     hflag.as<int32_t>(), s.scratch.as<int>());
+  s.launches += 1;
+  RET(inclusive_sum(errp, s, tmp, flag.as<int32_t>(), gincl.as<int32_t>(), n));
+  RET(inclusive_sum(errp, s, tmp, hflag.as<int32_t>(), hincl.as<int32_t>(), n));
+  int32_t n_groups32 = 0, n_heads32 = 0, bad = 0;
+  CK(cudaMemcpyAsync(&n_groups32, gincl.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(&n_heads32, hincl.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaMemcpyAsync(&bad, s.scratch.p, 4, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  if (bad) return fail(errp, ADEPT_CUDA_ERR_CUDA, "fused stream: an LHS reference does not open its group (schedule violates WAR/RAW)");
+  const int64_t n_groups = n_groups32;
+  s.R_f = n + int64_t(n_heads32);
+  if (s.R_f >= (int64_t(1) << 31) - 1) return fail(errp, ADEPT_CUDA_ERR_LIMIT, "fused stream too long");
+  RET(ensure(errp, s.ftgt, size_t(s.R_f) * sizeof(Rec)));
+  RET(ensure(errp, goff, size_t(n_groups + 1) * 8));
+  RET(ensure(errp, gstep, size_t(n_groups + 1) * 4));
+  fused_emit_kernel<<<grid_for(n, T, s.sm_count), T, 0, s.stream>>>(
+      s.stmt.as<int2>(), s.n_stmt, s.mult.as<double>(), s.idx.as<int32_t>(), O, k0.as<uint32_t>(), v0.as<uint32_t>(),
+      flag.as<int32_t>(), hflag.as<int32_t>(), gincl.as<int32_t>(), hincl.as<int32_t>(), n, par.as<uint8_t>(), G,
+      s.ftgt.as<Rec>(), goff.as<int64_t>(), gstep.as<int32_t>());
+  s.launches += 1;
+  CK(cudaMemcpyAsync(goff.as<int64_t>() + n_groups, &s.R_f, 8, cudaMemcpyHostToDevice, s.stream));
+  std::vector<int64_t> step_group_unused;
+  RET(build_group_tables(s, n_groups, s.R_f, goff.as<int64_t>(), gstep.as<int32_t>(), s.fchunk, &s.n_fchunks, step_group_unused,
+                         s.step_fchunk, nullptr));
+  CK(cudaGetLastError());
+  s.stat["an_fused_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  s.stat["fused_records"] = double(s.R_f);
+  s.have_fused = true;
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // Replay drivers
@@ -744,7 +885,7 @@ int mark(Shard& s) {
 
 // One sweep over the resident pass (g already zeroed and seeded).  mode: 0 forward, 1 reverse.
 int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t K, int64_t n_dirs,
-                 const SweepPlan& plan) {
+                 const SweepPlan& plan, bool fused) {
   std::string* errp = &s.err;
   if (s.R == 0) return 0;
   ReplayArgs A{};
@@ -841,15 +982,17 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       }
     }
   } else {
-    // reverse: steps downwards; per step snapshot a_s and zero the LHS slots, then gather per target
+    // reverse: steps downwards.  Fused: one kernel per step over versioned rows (reverse_fused_kernel).  Otherwise:
+    // per step snapshot a_s and zero the LHS slots, then gather per target.
     constexpr int V = 2;   // a lane owns two adjacent directions: 16-byte row accesses
+    if (!fused) RET(ensure_target_stream(c, s));
     TargetArgs B;
-    B.recs = s.tgt.as<Rec>();
-    B.chunk_begin = s.tchunk.as<int64_t>();
+    B.recs = (fused ? s.ftgt : s.tgt).as<Rec>();
+    B.chunk_begin = (fused ? s.fchunk : s.tchunk).as<int64_t>();
     B.g = g;
-    B.abuf = s.abuf.as<double>();
+    B.abuf = fused ? nullptr : s.abuf.as<double>();
     B.rowact = s.rowact.as<uint8_t>();
-    B.aflag = s.aflag.as<uint8_t>();
+    B.aflag = fused ? nullptr : s.aflag.as<uint8_t>();
     B.K = K;
     B.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
     B.flag_pitch = int(K / (32 * V));
@@ -862,7 +1005,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     if (!c->opt_persistent && B.n_colblocks >= 16 && B.n_colblocks / twarps < c->opt_streams)
       twarps = std::max(1, std::min(twarps, B.n_colblocks / std::max(1, c->opt_streams)));
     const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
-    if (c->opt_persistent && s.n_tchunks > 0) {
+    if (!fused && c->opt_persistent && s.n_tchunks > 0) {
       // one cooperative kernel walks all steps (persistent_kernels.cuh)
       PersistArgs PA;
       PA.T = B;
@@ -890,7 +1033,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const int all_cb = B.n_colblocks;
     int nstr = std::max(1, std::min<int>(c->opt_streams, (all_cb + twarps - 1) / twarps));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    if (double(s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + twarps - 1) / twarps) >= kWideStepCtas ||
+    if (double(fused ? s.n_fchunks : s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + twarps - 1) / twarps) >= kWideStepCtas ||
         c->opt_time_kernels)
       nstr = 1;
     while (int(s.aux.size()) < nstr - 1) {
@@ -924,6 +1067,16 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       for (int32_t l = s.n_levels; l >= 1; --l) {
         const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
         if (n <= 0) continue;
+        if (fused) {
+          const int64_t c0 = s.step_fchunk[l], c1 = s.step_fchunk[l + 1];
+          if (c1 <= c0) continue;
+          Bi.first_chunk = c0;
+          if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+          launch_pdl(reverse_fused_kernel<V>, dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), dim3(twarps * 32), st, pdl, Bi);
+          if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+          nl[i] += 1;
+          continue;
+        }
         const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
         launch_pdl(reverse_snapshot_kernel<V, 4>, dim3(unsigned((n * ncols + 255) / 256)), dim3(256), st, pdl,
                    s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
@@ -987,6 +1140,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     if (need(32) <= kSmemCap) dc = 32;
     if (need(64) <= kSmemCap && (D + 31) / 32 > 2 * s.sm_count) dc = 64;
     if (dc) {
+      if (mode == 1) RET(ensure_target_stream(c, s));
       SmallGArgs G;
       G.fwd = s.fwd_l.as<Rec>();
       G.foff = s.foff.as<int64_t>();
@@ -1034,43 +1188,63 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     }
   }
   if (D > 0) {
+    // fused reverse sweep: two rows per slot and no snapshot buffer
+    const SweepPlan plan0 = plan_sweep(c, s, D);
+    const bool fused = plan0.use_levels && mode == 1 && c->opt_fused && !c->opt_persistent && s.n_ops > 0 &&
+                       s.max_gradient < (int64_t(1) << 30);
+    const int64_t n_rows = fused ? 2 * s.max_gradient : s.max_gradient;
+    // the reverse stream this sweep needs (built on first use; before the workspace is sized, since it takes memory)
+    if (fused) RET(ensure_fused_stream(c, s));
+    else if (plan0.use_levels && mode == 1) RET(ensure_target_stream(c, s));
     // pass size from the workspace budget
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget =
         c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes) : size_t(double(free_b + s.g.bytes + s.abuf.bytes) * 0.6);
-    // per direction: a gradient column plus (reverse, level schedule) a column of the a-snapshot buffer
-    int64_t max_dirs = int64_t(budget / (size_t(s.max_gradient + s.max_step_width) * 8));
+    // per direction: a gradient column plus (reverse, two-kernel level sweep) a column of the a-snapshot buffer
+    int64_t max_dirs = int64_t(budget / (size_t(n_rows + (fused ? 0 : s.max_step_width)) * 8));
     max_dirs = (max_dirs / 32) * 32;
     if (max_dirs < 32) max_dirs = 32;
     int64_t pass = std::min<int64_t>(((D + 31) / 32) * 32, max_dirs);
+    if (pass < D) {  // several passes: make them equal
+      const int64_t np = (D + pass - 1) / pass;
+      pass = std::min(pass, (((D + np - 1) / np + 63) / 64) * 64);
+    }
     if (c->opt_pass_dirs > 0) pass = std::min<int64_t>(pass, ((c->opt_pass_dirs + 31) / 32) * 32);
     const int64_t K = ((pass + 63) / 64) * 64;   // rows padded so that 16-byte lane vectors never leave a row
-    RET(ensure(errp, s.g, size_t(s.max_gradient) * size_t(K) * 8));
+    RET(ensure(errp, s.g, size_t(n_rows) * size_t(K) * 8));
     double* g = s.g.as<double>();
     int n_passes = 0;
     const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
     const int V = 2;                               // doubles per lane in the level-reverse kernels
     const int ncb_pass = int(K / (32 * V));
     const bool sparse = plan.use_levels;
+    const int32_t* out_rows_dev = out_slots_dev;
     if (sparse) {
-      if (mode == 1) RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
-      RET(ensure(errp, s.rowact, size_t(s.max_gradient) * size_t(ncb_pass)));
-      RET(ensure(errp, s.aflag, size_t(std::max<int64_t>(s.max_step_width, 1)) * size_t(ncb_pass)));
+      if (mode == 1 && !fused) RET(ensure(errp, s.abuf, size_t(s.max_step_width) * size_t(K) * 8));
+      RET(ensure(errp, s.rowact, size_t(n_rows) * size_t(ncb_pass)));
+      if (!fused) RET(ensure(errp, s.aflag, size_t(std::max<int64_t>(s.max_step_width, 1)) * size_t(ncb_pass)));
+    }
+    if (fused) {  // the swept value of slot X ends up in row X + fpar[X]*G
+      RET(ensure(errp, s.out_rows, size_t(n_out) * 4));
+      fused_out_rows_kernel<<<unsigned((n_out + 255) / 256), 256, 0, s.stream>>>(out_slots_dev, n_out, s.fpar.as<uint8_t>(),
+                                                                                 s.max_gradient, s.out_rows.as<int32_t>());
+      s.launches += 1;
+      out_rows_dev = s.out_rows.as<int32_t>();
     }
     for (int64_t d0 = d_lo; d0 < d_hi; d0 += pass) {
       const int64_t n = std::min(pass, d_hi - d0);
       const bool last = d0 + pass >= d_hi;
-      CK(cudaMemsetAsync(g, 0, size_t(s.max_gradient) * size_t(K) * 8, s.stream));
-      if (sparse) CK(cudaMemsetAsync(s.rowact.p, 0, size_t(s.max_gradient) * size_t(ncb_pass), s.stream));
+      CK(cudaMemsetAsync(g, 0, size_t(n_rows) * size_t(K) * 8, s.stream));
+      if (sparse) CK(cudaMemsetAsync(s.rowact.p, 0, size_t(n_rows) * size_t(ncb_pass), s.stream));
       seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n),
                                                                     sparse ? s.rowact.as<uint8_t>() : nullptr, ncb_pass, 32 * V);
       s.launches += 1;
       if (last) CK(cudaEventRecord(s.ev[2], s.stream));
-      RET(launch_sweep(c, s, mode, g, K, n, plan));
+      RET(launch_sweep(c, s, mode, g, K, n, plan, fused));
       if (last) CK(cudaEventRecord(s.ev[3], s.stream));
       const dim3 eg(unsigned((n + 31) / 32), unsigned((n_out + 31) / 32));
-      extract_kernel<<<eg, dim3(32, 8), 0, s.stream>>>(g, K, out_slots_dev, n_out, int(n), d0 - d_base, out,
+      extract_kernel<<<eg, dim3(32, 8), 0, s.stream>>>(g, K, out_rows_dev, n_out, int(n), d0 - d_base, out,
                                                         stride_i, stride_d);
       s.launches += 1;
       ++n_passes;
@@ -1078,6 +1252,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     s.stat["pass_dirs"] = double(pass);
     s.stat["n_passes"] = double(n_passes);
     s.stat["used_schedule"] = plan.use_levels ? 2.0 : 1.0;
+    s.stat["used_fused"] = fused ? 1.0 : 0.0;
     s.stat["warps_per_cta"] = double(plan.warps);
   }
   CK(cudaEventRecord(s.ev[1], s.stream));
@@ -1366,6 +1541,7 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
           }
         }
       } else {
+        if (int rc = ensure_target_stream(c, s)) { c->err = s.err; return rc; }
         RET(ensure(errp, s.a1, size_t(std::max<int64_t>(s.max_step_width, 1)) * 8));
         for (int32_t l = s.n_levels; l >= 1; --l) {
           const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
@@ -1415,7 +1591,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.pos_in_sched, &s.ftgt, &s.fchunk, &s.fpar, &s.out_rows, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -1808,6 +1984,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_streams = int(value);
   } else if (k == "smallg") {
     c->opt_smallg = value ? 1 : 0;
+  } else if (k == "fused") {
+    c->opt_fused = value ? 1 : 0;
   } else if (k == "chunk_recs") {
     if (value < 0 || value > 256) return fail(errp, ADEPT_CUDA_ERR_ARG, "chunk_recs must be in 0..256");
     c->opt_chunk_recs = value;

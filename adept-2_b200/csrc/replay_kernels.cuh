@@ -507,6 +507,159 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Level-scheduled reverse sweep, one step = ONE kernel (tape_kernels.cuh, "FUSED reverse stream").
+// The workspace has 2*G rows (two per slot); records name physical rows.  Per target group:
+//   MARK(row)   acc = g[row]   (the target's live row, updated in place)
+//   ZMARK(row)  acc = +0.0     (the target is an LHS of this step: its NEW version goes to its other row)
+//   OP(m, arow) acc += m * g[arow]   (arow = live row of the contributing statement's LHS, i.e. a_s)
+// Within a step no row is both read by one group and written by another, so all loads of a step are
+// independent of all its stores and one launch per step suffices.  rowact[row*ncb + cb] == 0 means the
+// block is all +0.0 whatever the (possibly stale) memory holds; a ZMARK's bytes are cleared by the CTA
+// that stages it, for all the column blocks the CTA owns, before any warp may set them again.
+// Against snapshot + gather this saves a launch per step and, per statement and direction, the 8-byte
+// read + 8-byte zero store of g[lhs] and the 8-byte write of the a_s copy.
+// ---------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256, 3) reverse_fused_kernel(TargetArgs A) {
+  __shared__ StageRing ring;
+  __shared__ uint8_t pf[kPieceRecs][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t c = A.first_chunk + blockIdx.x;
+  const int64_t r0 = A.chunk_begin[c], r1 = A.chunk_begin[c + 1];
+  const int64_t n_recs = r1 - r0;
+  const Rec* chunk = A.recs + r0;
+  const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
+  const int cb0 = A.cb_lo + blockIdx.y * nwarps;
+  const int cb = cb0 + warp;
+  const int ncb = A.flag_pitch;
+  const bool live = cb < A.n_colblocks;
+  const int64_t d0 = (static_cast<int64_t>(cb) * 32 + lane) * V;  // first direction of this lane; rows are padded to K
+  const bool ok0 = d0 < A.n_dirs, ok1 = d0 + 1 < A.n_dirs;
+  double* gcol = A.g + d0;
+  uint8_t* ract = A.rowact + cb;
+  const uint32_t P = static_cast<uint32_t>(A.ref_block);
+  const uint32_t lanes_per_grp = (V == 2) ? (P >= 2 ? P / 2 : 1) : P;
+  const uint32_t grp_mask =
+      (lanes_per_grp >= 32 ? 0xffffffffu : ((1u << lanes_per_grp) - 1u)) << ((lane / lanes_per_grp) * lanes_per_grp);
+  const bool per_component = (V == 2 && P == 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_trigger();
+  if (threadIdx.x == 0)
+    for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
+  pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
+
+  LaneVec<V> acc;
+  acc.zero();
+  int32_t cur = -1;        // row whose sum is (or will be) in acc
+  bool cur_zero = false;   // the open group began with a ZMARK (its sum starts from +0.0)
+  bool acc_valid = false;  // acc holds the start value of cur (+ contributions)
+  bool dirty = false;      // acc differs from what memory holds
+  for (int64_t p = 0; p < n_pieces; ++p) {
+    const int st = static_cast<int>(p % kStages);
+    mbar_wait(&ring.full[st], static_cast<uint32_t>((p / kStages) & 1));
+    const int64_t left = n_recs - p * kPieceRecs;
+    const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
+    const Rec* r = &ring.buf[st][0];
+    // 1. activity bytes of the piece: thread t -> record t / nwarps, column block cb0 + t % nwarps
+    for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
+      const int i = t / nwarps, w = t - i * nwarps;
+      const int32_t row = r[i].slot;
+      uint8_t f = 0;
+      if (cb0 + w < A.n_colblocks && row >= 0) {
+        uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
+        if (r[i].kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
+        else f = *b;
+      }
+      pf[i][w] = f;
+    }
+    __syncthreads();
+    if (live) {
+      bool mine = false;
+      for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[i][warp] != 0);
+      if (!__any_sync(0xffffffffu, mine)) {
+        // nothing to add: retire the open target; remember the last head for a group that goes on
+        if (dirty) {
+          acc.store(gcol + static_cast<int64_t>(cur) * A.K);
+          if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+          dirty = false;
+        }
+        int last = -1;
+        for (int i = lane; i < n; i += 32)
+          if (r[i].kind != REC_OP) last = i;
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (last >= 0) {
+          cur = r[last].slot;
+          cur_zero = (r[last].kind == REC_ZMARK);
+          acc_valid = false;
+        }
+      } else {
+        for (int i = 0; i < n; i += kBatch) {
+          LaneVec<V> v[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            v[u].zero();
+            if (i + u < n && pf[i + u][warp]) v[u].load(gcol + static_cast<int64_t>(r[i + u].slot) * A.K);
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (i + u >= n) break;
+            const Rec rc = r[i + u];
+            if (rc.kind != REC_OP) {  // next target: retire the previous one
+              if (dirty) {
+                acc.store(gcol + static_cast<int64_t>(cur) * A.K);
+                if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+              }
+              cur = rc.slot;
+              cur_zero = (rc.kind == REC_ZMARK);
+              acc = v[u];  // +0.0 for a ZMARK and for an inactive live row
+              acc_valid = true;
+              dirty = false;
+            } else if (pf[i + u][warp]) {
+              if (!acc_valid) {  // the group began in a piece this warp skipped
+                acc.zero();
+                if (!cur_zero && ract[static_cast<int64_t>(cur) * ncb]) acc.load(gcol + static_cast<int64_t>(cur) * A.K);
+                acc_valid = true;
+              }
+              if (V == 1) {
+                const uint32_t nz = __ballot_sync(0xffffffffu, ok0 && v[u].x != 0.0);
+                if ((nz & grp_mask) != 0u) acc.x = mul_add_rn(acc.x, rc.m, v[u].x);
+              } else {
+                double* av = reinterpret_cast<double*>(&v[u]);
+                double* cv = reinterpret_cast<double*>(&acc);
+                const bool n0 = ok0 && av[0] != 0.0, n1 = ok1 && av[V - 1] != 0.0;
+                bool act0, act1;
+                if (per_component) {
+                  act0 = n0;
+                  act1 = n1;
+                } else {
+                  const uint32_t nz = __ballot_sync(0xffffffffu, n0 || n1);
+                  act0 = act1 = (nz & grp_mask) != 0u;
+                }
+                if (act0) cv[0] = mul_add_rn(cv[0], rc.m, av[0]);
+                if (act1) cv[V - 1] = mul_add_rn(cv[V - 1], rc.m, av[V - 1]);
+              }
+              dirty = true;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
+  }
+  if (live && dirty) {
+    acc.store(gcol + static_cast<int64_t>(cur) * A.K);
+    if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Level-scheduled forward sweep (one launch per step): statements of a step are mutually
 // independent gathers, so loads are batched freely.  Same CTA shape, TMA staging, lane vectors
 // and block-sparsity bytes as reverse_target_kernel: a statement whose operand blocks are all

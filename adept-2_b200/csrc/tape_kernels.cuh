@@ -722,6 +722,154 @@ __global__ void target_step_tables_kernel(int64_t* __restrict__ step_group, int3
   step_tchunk[0] = 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// FUSED reverse stream ("versioned rows"): one kernel per step instead of snapshot + gather.
+//
+// Every slot X owns two physical rows, row(X, p) = X + p*G.  The live value of X sits in row(X, p)
+// with p = (number of statements LATER in the tape whose LHS is X) mod 2: the live row flips each time
+// the reverse sweep passes a writer of X.  A step then only READS live rows and WRITES either a
+// target's own live row in place (X is not an LHS of the step, so no other target of the step reads
+// it) or the OTHER row of an LHS slot, so that a_s = g[row(lhs_s, p)] stays intact for every target of
+// the step that still needs it:
+//     ZMARK(row(lhs_s, p^1))  OP(m, row(lhs_s, p))*      target X = lhs_s: starts from +0.0; only
+//                                                         self references of s can follow
+//     MARK (row(X, p))        OP(m, row(lhs_s', p'))*    any other target: starts from its live value
+// Per slot the contributions keep the reference's order (statement descending, operand ascending;
+// adept/jacobian.cpp:410-428) exactly as in the two-kernel form.  tests/test_fused_stream_model.py is
+// the sequential statement of this construction, checked against the oracle.
+//
+// Elements are the R = O + S references of the tape in the reference's reverse sweep order; element
+// id: operation o -> o, LHS of statement s -> O + (s-1).
+// ---------------------------------------------------------------------------------------
+__global__ void fused_keys_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ idx,
+                                  int64_t n_ops, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const int64_t S = n_stmt - 1;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = t; o < n_ops; o += stride) {
+    const int64_t s = stmt_of_op(stmt, n_stmt, o);
+    const int64_t pos = (S - s) + (n_ops - stmt[s].y) + 1 + (o - stmt[s - 1].y);
+    key[pos] = static_cast<uint32_t>(idx[o]);
+    val[pos] = static_cast<uint32_t>(o);
+  }
+  for (int64_t s = 1 + t; s < n_stmt; s += stride) {
+    const int64_t pos = (S - s) + (n_ops - stmt[s].y);
+    key[pos] = static_cast<uint32_t>(stmt[s].x);
+    val[pos] = static_cast<uint32_t>(n_ops + (s - 1));
+  }
+}
+// isl[i] = 1 when element i is an LHS reference
+__global__ void fused_islhs_kernel(const uint32_t* __restrict__ val, int64_t n, int64_t n_ops, int32_t* __restrict__ isl) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride) isl[i] = (static_cast<int64_t>(val[i]) >= n_ops) ? 1 : 0;
+}
+// elements sorted by (slot, sweep order); E = exclusive scan of isl.  e0[slot] = E at the slot's first element.
+__global__ void fused_segstart_kernel(const uint32_t* __restrict__ key, const int32_t* __restrict__ E, int64_t n,
+                                      int32_t* __restrict__ e0) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride)
+    if (i == 0 || key[i] != key[i - 1]) e0[key[i]] = E[i];
+}
+// par[id] = (writers of the element's slot already passed by the sweep) & 1; fpar[slot] = parity after the sweep
+__global__ void fused_parity_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                                    const int32_t* __restrict__ isl, const int32_t* __restrict__ E,
+                                    const int32_t* __restrict__ e0, int64_t n, uint8_t* __restrict__ par,
+                                    uint8_t* __restrict__ fpar) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride) {
+    const uint32_t x = key[i];
+    const int32_t cnt = E[i] - e0[x];
+    par[val[i]] = static_cast<uint8_t>(cnt & 1);
+    if (i == n - 1 || key[i + 1] != x) fpar[x] = static_cast<uint8_t>((cnt + isl[i]) & 1);
+  }
+}
+__device__ __forceinline__ int64_t fused_stmt_of(const int2* __restrict__ stmt, int64_t n_stmt, int64_t n_ops, int64_t id) {
+  return id < n_ops ? stmt_of_op(stmt, n_stmt, id) : id - n_ops + 1;
+}
+// second sort key: the step of the element's statement
+__global__ void fused_step_keys_kernel(const int2* __restrict__ stmt, int64_t n_stmt, int64_t n_ops,
+                                       const uint32_t* __restrict__ val, int64_t n, const int32_t* __restrict__ level,
+                                       uint32_t* __restrict__ key) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride) key[i] = static_cast<uint32_t>(level[fused_stmt_of(stmt, n_stmt, n_ops, val[i])]);
+}
+__device__ __forceinline__ int32_t fused_slot_of(const int2* __restrict__ stmt, const int32_t* __restrict__ idx,
+                                                 int64_t n_ops, int64_t id) {
+  return id < n_ops ? idx[id] : stmt[id - n_ops + 1].x;
+}
+// elements sorted by (step, slot, sweep order): flag = a new (step, slot) group; hflag = the group needs an
+// inserted MARK head (it opens with an operation; an LHS reference is its own head)
+__global__ void fused_flags_kernel(const int2* __restrict__ stmt, const int32_t* __restrict__ idx, int64_t n_ops,
+                                   const uint32_t* __restrict__ step_key, const uint32_t* __restrict__ val, int64_t n,
+                                   int32_t* __restrict__ flag, int32_t* __restrict__ hflag, int* __restrict__ bad) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride) {
+    int f = 0;
+    if (i == 0 || step_key[i] != step_key[i - 1] ||
+        fused_slot_of(stmt, idx, n_ops, val[i]) != fused_slot_of(stmt, idx, n_ops, val[i - 1]))
+      f = 1;
+    const bool is_op = static_cast<int64_t>(val[i]) < n_ops;
+    flag[i] = f;
+    hflag[i] = (f && is_op) ? 1 : 0;
+    if (!is_op && !f) atomicOr(bad, 1);   // cannot happen with a schedule that obeys RAW/WAR/WAW
+  }
+}
+// emit the stream; gincl/hincl = inclusive scans of flag/hflag.  goff[g] = record offset of group g's head,
+// gstep[g] = its step.
+__global__ void fused_emit_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const double* __restrict__ mult,
+                                  const int32_t* __restrict__ idx, int64_t n_ops, const uint32_t* __restrict__ step_key,
+                                  const uint32_t* __restrict__ val, const int32_t* __restrict__ flag,
+                                  const int32_t* __restrict__ hflag, const int32_t* __restrict__ gincl,
+                                  const int32_t* __restrict__ hincl, int64_t n, const uint8_t* __restrict__ par,
+                                  int64_t G, Rec* __restrict__ out, int64_t* __restrict__ goff,
+                                  int32_t* __restrict__ gstep) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = t; i < n; i += stride) {
+    const int64_t id = val[i];
+    const int64_t pos = i + hincl[i];
+    const int64_t s = fused_stmt_of(stmt, n_stmt, n_ops, id);
+    const int64_t lhs = stmt[s].x;
+    const int64_t lp = par[n_ops + s - 1];     // parity of the LHS's live row when the sweep reaches s
+    Rec r;
+    if (id < n_ops) {
+      r.m = mult[id];
+      r.slot = static_cast<int32_t>(lhs + lp * G);
+      r.kind = REC_OP;
+      out[pos] = r;
+      if (hflag[i]) {
+        Rec h;
+        h.m = 0.0;
+        h.slot = static_cast<int32_t>(static_cast<int64_t>(idx[id]) + static_cast<int64_t>(par[id]) * G);
+        h.kind = REC_MARK;
+        out[pos - 1] = h;
+        goff[gincl[i] - 1] = pos - 1;
+        gstep[gincl[i] - 1] = static_cast<int32_t>(step_key[i]);
+      }
+    } else {
+      r.m = 0.0;
+      r.slot = static_cast<int32_t>(lhs + (lp ^ 1) * G);
+      r.kind = REC_ZMARK;
+      out[pos] = r;
+      if (flag[i]) {
+        goff[gincl[i] - 1] = pos;
+        gstep[gincl[i] - 1] = static_cast<int32_t>(step_key[i]);
+      }
+    }
+  }
+}
+// rows[i] = slot[i] + fpar[slot[i]]*G: where the swept value of each output slot ends up
+__global__ void fused_out_rows_kernel(const int32_t* __restrict__ slot, int64_t n, const uint8_t* __restrict__ fpar,
+                                      int64_t G, int32_t* __restrict__ rows) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) rows[i] = static_cast<int32_t>(static_cast<int64_t>(slot[i]) + static_cast<int64_t>(fpar[slot[i]]) * G);
+}
+
 // per-step table for the shared-memory-resident kernel: {first item, end item, first record, end record}
 __global__ void step_info_kernel(const int64_t* __restrict__ first, const int64_t* __restrict__ off, int32_t n_levels,
                                  longlong4* __restrict__ info) {

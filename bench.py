@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--persistent", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--fused", type=int, default=1, help="reverse level sweep as one kernel per step (0: snapshot + gather)")
     args = ap.parse_args()
     if args.workload in ("rosenbrock1e7", "ensemble1e5"):
         return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
@@ -337,6 +338,7 @@ def main():
     eng.set_option("warps_per_cta", args.warps)
     eng.set_option("persistent", args.persistent)
     eng.set_option("chunk_recs", args.chunk)
+    eng.set_option("fused", args.fused)
     if args.streams:
         eng.set_option("streams", args.streams)
 
@@ -409,6 +411,7 @@ def main():
     dom_ms, dom_launches = eng.stat("dominant_ms", 0.0), eng.stat("dominant_launches", 0.0)
     sweep_ms = eng.stat("sweep_ms", 0.0)
     used = eng.stat("used_schedule", 0.0)
+    used_fused = bool(eng.stat("used_fused", 0.0)) and used == 2 and mode == 1
     eng.set_option("time_kernels", 0)
 
     # end to end through the C-ABI with host buffers: H2D of the tape + schedule build + replay + D2H
@@ -432,7 +435,7 @@ def main():
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
         phases["upload_call_ms"] = 1e3 * t_up / args.e2e_steps
         phases["jacobian_call_ms"] = 1e3 * t_jac / args.e2e_steps
-        for k in ("upload_ms", "analysis_ms", "an_window_ms", "an_forward_ms", "an_target_ms", "bcast_ms", "replay_ms",
+        for k in ("upload_ms", "analysis_ms", "an_window_ms", "an_forward_ms", "an_target_ms", "an_fused_ms", "bcast_ms", "replay_ms",
                   "d2h_ms", "jacobian_wall_ms", "upload_total_ms"):
             phases[k] = eng.stat(k, None)
         e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -466,13 +469,16 @@ def main():
     peak, peak_src = peaks()
     bpo = alg_bytes_per_opdir(S, O, mode)
     # algorithmic bytes of the dominant kernel: the per-operation part (reverse: 16 B, forward: 8 B per op*dir;
-    # the per-statement part belongs to the snapshot kernel / the TAIL stores)
-    dom_bytes = (16.0 if mode else 8.0) * work / world if used == 2 and mode == 1 else bpo * work / world
+    # the per-statement part belongs to the snapshot kernel / the TAIL stores); the fused reverse kernel does the
+    # per-statement part too, so it is credited with the whole formula
+    dom_bytes = 16.0 * work / world if used == 2 and mode == 1 and not used_fused else bpo * work / world
     roof = None
     if dom_ms and dom_launches:
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         kname = {(1, 2.0): "reverse_target_kernel<2>", (0, 2.0): "forward_level_kernel<2,sparse>", (1, 1.0): "replay_reverse_kernel",
                  (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
+        if used_fused:
+            kname[(1, 2.0)] = "reverse_fused_kernel<2>"
         roof = {"bound": "hbm", "kernel": kname.get((mode, used), "?"),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "launches_per_step": dom_launches,
@@ -485,7 +491,7 @@ def main():
     if roof is not None:
         try:   # DRAM traffic of one profiled launch (ncu --set full), when a capture for this workload is on file
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            if tr:
+            if tr and tr.get("kernel") == roof["kernel"]:
                 roof["traffic"] = tr["dram_bytes_per_launch"]
                 roof["traffic_sample"] = tr["launch"]
         except Exception:

@@ -13,11 +13,14 @@ from conftest import golden_names, load_golden, same_bits
 pytestmark = pytest.mark.gpu
 
 ORDERED, LEVELS, SMALLG = 1, 2, 3   # SMALLG: level schedule with the shared-memory-resident kernel allowed
+UNFUSED = 4                         # level schedule, reverse sweep as snapshot + gather (two kernels per step)
+                                    # instead of the fused one-kernel-per-step sweep over versioned rows (LEVELS)
 
 
 def upload(engine, t, schedule, window=0):
     engine.set_option("smallg", 1 if schedule in (0, SMALLG) else 0)
-    schedule = LEVELS if schedule == SMALLG else schedule
+    engine.set_option("fused", 0 if schedule == UNFUSED else 1)
+    schedule = LEVELS if schedule in (SMALLG, UNFUSED) else schedule
     engine.set_option("schedule", schedule)
     engine.set_option("window", window)
     engine.set_option("pass_dirs", 0)
@@ -36,14 +39,20 @@ def check_jacobians(engine, po, t, what=""):
 
 # ---- golden vectors (made by the real reference) --------------------------------------------------
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("schedule,window", [(ORDERED, 0), (LEVELS, 0), (LEVELS, 64), (LEVELS, 1000), (SMALLG, 0), (SMALLG, 64)])
+@pytest.mark.parametrize("schedule,window", [(ORDERED, 0), (LEVELS, 0), (LEVELS, 64), (LEVELS, 1000), (SMALLG, 0), (SMALLG, 64),
+                                             (UNFUSED, 0), (UNFUSED, 64)])
 def test_golden_jacobians(engine, name, schedule, window):
     g = load_golden(name)
     upload(engine, g, schedule, window)
     assert same_bits(engine.jacobian(0, g["indep"], g["dep"]), g["jac_fwd"]), "forward"
     assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"]), "reverse"
     used = engine.stat("used_schedule")
-    assert used == schedule or (schedule == SMALLG and used in (LEVELS, SMALLG))   # rosenbrock_n400 is too wide for smem
+    if schedule in (LEVELS, UNFUSED):
+        assert used == LEVELS
+        # tapes without operations have nothing to fuse; everything else must take the path the test names
+        assert engine.stat("used_fused") == (1 if schedule == LEVELS and g["idx"].size else 0)
+    else:
+        assert used == schedule or (schedule == SMALLG and used in (LEVELS, SMALLG))   # rosenbrock_n400 is too wide for smem
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -96,9 +105,12 @@ def test_random_tapes(engine, po, pkg, seed):
     t = pkg.tapegen.random_small_tape(rng, int(rng.integers(50, 6000)), int(rng.integers(8, 300)),
                                       n_indep=int(rng.integers(1, 70)) if seed else 1,
                                       n_dep=int(rng.integers(1, 7)))
-    for schedule, window in ((ORDERED, 0), (LEVELS, 0), (LEVELS, 97), (SMALLG, 97)):
+    for schedule, window in ((ORDERED, 0), (LEVELS, 0), (LEVELS, 97), (SMALLG, 97), (UNFUSED, 97)):
         upload(engine, t, schedule, window)
         check_jacobians(engine, po, t, f"seed {seed} schedule {schedule} window {window}")
+        engine.set_option("pass_dirs", 32)                       # several passes through the same stream
+        check_jacobians(engine, po, t, f"seed {seed} schedule {schedule} window {window} passes")
+        engine.set_option("pass_dirs", 0)
         g0 = rng.uniform(-1, 1, t["max_gradient"])
         flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
         assert same_bits(engine.adjoint(g0, True, flags), po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
@@ -137,7 +149,7 @@ def test_offsets(engine, po, pkg):
 
 def test_multiple_passes(engine, po, pkg):
     t = pkg.tapegen.advection_tape("lw", 100, 30)
-    for schedule in (ORDERED, LEVELS):
+    for schedule in (ORDERED, LEVELS, UNFUSED):
         upload(engine, t, schedule)
         engine.set_option("pass_dirs", 32)        # 100 directions -> 4 passes, the last one partial
         check_jacobians(engine, po, t, f"passes schedule {schedule}")
@@ -175,7 +187,7 @@ def test_non_finite_multipliers_follow_the_reference_block_rule(engine, po, pkg,
     t = pkg.tapegen.random_small_tape(rng, 500, 40, n_indep=6, n_dep=9)
     t["mult"][rng.integers(0, t["mult"].size, 12)] = np.inf
     t["mult"][rng.integers(0, t["mult"].size, 6)] = np.nan
-    for schedule in (ORDERED, LEVELS, SMALLG):
+    for schedule in (ORDERED, LEVELS, SMALLG, UNFUSED):
         upload(engine, t, schedule, 64)
         engine.set_option("ref_block", P)
         for mode in (0, 1):
@@ -198,12 +210,12 @@ def test_thread_safe_workload(engine, po, pkg):
         t = pkg.tapegen.advection_tape("toon", 128, 200)
         want = {m: po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], m)[1]
                 for m in (0, 1)}
-    for schedule in (ORDERED, LEVELS, SMALLG):
+    for schedule in (ORDERED, LEVELS, SMALLG, UNFUSED):
         upload(engine, t, schedule)
         jf = engine.jacobian(0, t["indep"], t["dep"])
         jr = engine.jacobian(1, t["indep"], t["dep"])
         assert same_bits(jf, want[0]) and same_bits(jr, want[1])
-        assert engine.stat("used_schedule") == schedule
+        assert engine.stat("used_schedule") == (LEVELS if schedule == UNFUSED else schedule)
         assert np.sqrt(np.mean((jf - jr) ** 2)) <= 1e-5
 
 
@@ -232,9 +244,11 @@ def test_rosenbrock_adjoint_with_a_long_statement(engine, po, pkg):
 def test_synthetic_config4_shape(engine, po, pkg):
     """BASELINE config 4 at reduced length: 2e5 statements, 2^14 slots, 256x256; parity on the full matrix."""
     t = pkg.tapegen.synthetic_tape(200_000, 14, 256, seed=42)
-    upload(engine, t, LEVELS)
-    check_jacobians(engine, po, t, "synthetic")
-    assert engine.stat("used_schedule") == LEVELS
+    for schedule in (LEVELS, UNFUSED):
+        upload(engine, t, schedule)
+        check_jacobians(engine, po, t, "synthetic")
+        assert engine.stat("used_schedule") == LEVELS
+        assert engine.stat("used_fused") == (1 if schedule == LEVELS else 0)
 
 
 # ---- size-independent properties at a size the oracle would not finish quickly ------------------------
