@@ -127,6 +127,7 @@ struct adept_cuda_ctx {
   int opt_streams = 4;  // CUDA streams over which the direction ranges of a level-scheduled reverse sweep are spread
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
+  int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -1002,9 +1003,19 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     // warps per CTA: with few column blocks (few directions on this GPU) use narrower CTAs so that there are still
     // several independent direction ranges to spread over the streams
     int twarps = std::max(1, std::min(plan.warps, B.n_colblocks));
-    if (!c->opt_persistent && B.n_colblocks >= 16 && B.n_colblocks / twarps < c->opt_streams)
+    if (!fused && !c->opt_persistent && B.n_colblocks >= 16 && B.n_colblocks / twarps < c->opt_streams)
       twarps = std::max(1, std::min(twarps, B.n_colblocks / std::max(1, c->opt_streams)));
     const unsigned tgy = unsigned((B.n_colblocks + twarps - 1) / twarps);
+    // fused kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
+    // groups are kept for the streams below
+    int cbs = kFusedCbs;
+    if (c->opt_cbs > 0) cbs = int(std::min<int64_t>(c->opt_cbs, kFusedCbs));
+    else if (B.n_colblocks < kFusedCbs * c->opt_streams)
+      cbs = std::max(std::min(8, B.n_colblocks), (B.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
+    cbs = std::max(1, std::min(cbs, kFusedCbs));
+    B.cbs = cbs;
+    if (fused) twarps = std::max(1, std::min(plan.warps, cbs));
+    const int gwidth = fused ? cbs : twarps;   // column blocks per CTA row
     if (!fused && c->opt_persistent && s.n_tchunks > 0) {
       // one cooperative kernel walks all steps (persistent_kernels.cuh)
       PersistArgs PA;
@@ -1031,9 +1042,9 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     // column blocks over a few CUDA streams so that the launch gap and the tail of one range's step are filled
     // by another range's kernels.
     const int all_cb = B.n_colblocks;
-    int nstr = std::max(1, std::min<int>(c->opt_streams, (all_cb + twarps - 1) / twarps));
+    int nstr = std::max(1, std::min<int>(c->opt_streams, (all_cb + gwidth - 1) / gwidth));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    if (double(fused ? s.n_fchunks : s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + twarps - 1) / twarps) >= kWideStepCtas ||
+    if (double(fused ? s.n_fchunks : s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + gwidth - 1) / gwidth) >= kWideStepCtas ||
         c->opt_time_kernels)
       nstr = 1;
     while (int(s.aux.size()) < nstr - 1) {
@@ -1050,7 +1061,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     }
     // column groups (of twarps blocks) per stream; one host thread per stream issues that stream's launches
     // (thousands of small launches per sweep: a single thread would be the bottleneck)
-    const int groups = (all_cb + twarps - 1) / twarps;
+    const int groups = (all_cb + gwidth - 1) / gwidth;
     std::vector<int> rcs(nstr, 0);
     std::vector<double> nl(nstr, 0.0);
     const bool pdl = c->opt_pdl && !c->opt_time_kernels;
@@ -1058,7 +1069,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       if (cudaSetDevice(s.dev) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
       const int g_lo = int(int64_t(groups) * i / nstr), g_hi = int(int64_t(groups) * (i + 1) / nstr);
       if (g_hi <= g_lo) return;
-      const int cb_lo = g_lo * twarps, cb_hi = std::min(all_cb, g_hi * twarps);
+      const int cb_lo = g_lo * gwidth, cb_hi = std::min(all_cb, g_hi * gwidth);
       cudaStream_t st = (i == 0) ? s.stream : s.aux[i - 1];
       const int ncols = cb_hi - cb_lo;
       TargetArgs Bi = B;
@@ -1072,7 +1083,10 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
           if (c1 <= c0) continue;
           Bi.first_chunk = c0;
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-          launch_pdl(reverse_fused_kernel<V>, dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), dim3(twarps * 32), st, pdl, Bi);
+          const dim3 fgrid(unsigned(c1 - c0), unsigned(g_hi - g_lo)), fblock(twarps * 32);
+          if (B.ref_block == 1) launch_pdl(reverse_fused_kernel<V, 0>, fgrid, fblock, st, pdl, Bi);
+          else if (B.ref_block == 2) launch_pdl(reverse_fused_kernel<V, 1>, fgrid, fblock, st, pdl, Bi);
+          else launch_pdl(reverse_fused_kernel<V, 2>, fgrid, fblock, st, pdl, Bi);
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           nl[i] += 1;
           continue;
@@ -1271,12 +1285,15 @@ int shard_finish(Shard& s) {
   s.stat["sweep_ms"] = ms;                        // the replay kernels of the LAST pass alone
   // dominant kernel (forward: replay_forward_kernel, reverse: reverse_target_kernel / replay_reverse_kernel),
   // every launch timed on its own when "time_kernels" is on
-  double dom = 0;
+  double dom = 0, dq[4] = {0, 0, 0, 0};
+  const size_t n_dom = s.kev_used / 2;
   for (size_t k = 0; k + 1 < s.kev_used; k += 2) {
     CK(cudaEventElapsedTime(&ms, s.kev[k], s.kev[k + 1]));
     dom += ms;
+    dq[std::min<size_t>(3, (k / 2) * 4 / std::max<size_t>(n_dom, 1))] += ms;   // by quarter of the sweep, in issue order
   }
   s.stat["dominant_ms"] = dom;
+  for (int q = 0; q < 4; ++q) s.stat[std::string("dominant_q") + char('1' + q) + "_ms"] = dq[q];
   s.stat["dominant_launches"] = double(s.kev_used / 2);
   return 0;
 }
@@ -1986,6 +2003,9 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_smallg = value ? 1 : 0;
   } else if (k == "fused") {
     c->opt_fused = value ? 1 : 0;
+  } else if (k == "cbs") {
+    if (value < 0 || value > kFusedCbs) return fail(errp, ADEPT_CUDA_ERR_ARG, "cbs must be in 0..32");
+    c->opt_cbs = int(value);
   } else if (k == "chunk_recs") {
     if (value < 0 || value > 256) return fail(errp, ADEPT_CUDA_ERR_ARG, "chunk_recs must be in 0..256");
     c->opt_chunk_recs = value;

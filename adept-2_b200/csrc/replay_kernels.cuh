@@ -57,8 +57,9 @@ struct StageRing {
 };
 
 // Issue the TMA copy of piece `p` of the chunk into its ring slot.  One thread calls this.
-__device__ __forceinline__ void issue_piece(StageRing& ring, const Rec* chunk, int64_t n_recs, int64_t p) {
-  const int st = static_cast<int>(p % kStages);
+// `slot_seq` is the position in the ring's issue sequence when a chunk is streamed more than once (default: p).
+__device__ __forceinline__ void issue_piece(StageRing& ring, const Rec* chunk, int64_t n_recs, int64_t p, int64_t slot_seq = -1) {
+  const int st = static_cast<int>((slot_seq < 0 ? p : slot_seq) % kStages);
   const int64_t off = p * kPieceRecs;
   const int64_t left = n_recs - off;
   const uint32_t cnt = static_cast<uint32_t>(left < kPieceRecs ? left : kPieceRecs);
@@ -358,6 +359,7 @@ struct TargetArgs {
   int flag_pitch;    // row pitch of rowact/aflag
   int64_t n_dirs;
   int ref_block;
+  int cbs;           // reverse_fused_kernel: column blocks per CTA (<= kFusedCbs)
 };
 
 // The CTA first fetches, in one round trip and for all its warps, the activity byte of every
@@ -519,10 +521,203 @@ __global__ void __launch_bounds__(256, 3) reverse_target_kernel(TargetArgs A) {
 // Against snapshot + gather this saves a launch per step and, per statement and direction, the 8-byte
 // read + 8-byte zero store of g[lhs] and the 8-byte write of the a_s copy.
 // ---------------------------------------------------------------------------------------
+//
+// CTA shape.  A CTA owns one chunk of records and up to 32 column blocks (A.cbs).  Jacobians are
+// structurally sparse (a Toon row touches about a quarter of the (statement, column block) pairs, and the
+// reference skips the rest as well, adept/jacobian.cpp:392-407), so binding warp w to column block w would
+// leave most warps idle while a few walk the dependent round trips.  Instead the CTA reads the activity
+// bytes of all its (record, column block) pairs in one round trip, forms the mask of column blocks that
+// receive any contribution from the chunk, and its warps take the ACTIVE column blocks in turn.
+constexpr int kFusedCbs = 32;   // column blocks per CTA (<= 32: the activity mask is one word)
+
 template <int V>
+struct FusedState {
+  LaneVec<V> acc;
+  int32_t cur;     // row whose sum is (or will be) in acc
+  bool cur_zero;   // the open group began with a ZMARK (its sum starts from +0.0)
+  bool acc_valid;  // acc holds the start value of cur (+ contributions)
+  bool dirty;      // acc differs from what memory holds
+  __device__ __forceinline__ void reset() {
+    acc.zero();
+    cur = -1;
+    cur_zero = false;
+    acc_valid = false;
+    dirty = false;
+  }
+};
+
+struct FusedLane {
+  double* gcol;     // &g[0][first direction of this lane]
+  uint8_t* ract;    // &rowact[0][column block]
+  int64_t K;
+  int ncb;
+  int lane;
+  bool ok0, ok1;
+  uint32_t grp_mask;
+  bool per_component;
+};
+
+template <int V>
+__device__ __forceinline__ void fused_retire(FusedState<V>& S, const FusedLane& L) {
+  if (S.dirty) {
+    S.acc.store(L.gcol + static_cast<int64_t>(S.cur) * L.K);
+    if (L.lane == 0) L.ract[static_cast<int64_t>(S.cur) * L.ncb] = 1;
+    S.dirty = false;
+  }
+}
+
+// records [0, n) of a staged piece for ONE column block; pfw[i] = activity byte of record i there
+template <int V>
+__device__ __forceinline__ void fused_piece(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
+                                            FusedState<V>& S, const FusedLane& L) {
+  for (int i = 0; i < n; i += kBatch) {
+    LaneVec<V> v[kBatch];
+    // rows of the active records only; all loads of a step are independent of its stores
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      v[u].zero();
+      if (i + u < n && pfw[i + u]) v[u].load(L.gcol + static_cast<int64_t>(r[i + u].slot) * L.K);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (i + u >= n) break;
+      const Rec rc = r[i + u];   // re-read from shared memory: keeps the batch's registers for data
+      if (rc.kind != REC_OP) {   // next target: retire the previous one
+        fused_retire<V>(S, L);
+        S.cur = rc.slot;
+        S.cur_zero = (rc.kind == REC_ZMARK);
+        S.acc = v[u];  // +0.0 for a ZMARK and for an inactive live row
+        S.acc_valid = true;
+      } else if (pfw[i + u]) {
+        if (!S.acc_valid) {  // the group began in a piece this warp skipped
+          S.acc.zero();
+          if (!S.cur_zero && L.ract[static_cast<int64_t>(S.cur) * L.ncb]) S.acc.load(L.gcol + static_cast<int64_t>(S.cur) * L.K);
+          S.acc_valid = true;
+        }
+        if (V == 1) {
+          const uint32_t nz = __ballot_sync(0xffffffffu, L.ok0 && v[u].x != 0.0);
+          if ((nz & L.grp_mask) != 0u) S.acc.x = mul_add_rn(S.acc.x, rc.m, v[u].x);
+        } else {
+          double* av = reinterpret_cast<double*>(&v[u]);
+          double* cv = reinterpret_cast<double*>(&S.acc);
+          const bool n0 = L.ok0 && av[0] != 0.0, n1 = L.ok1 && av[V - 1] != 0.0;
+          bool act0, act1;
+          if (L.per_component) {
+            act0 = n0;
+            act1 = n1;
+          } else {
+            const uint32_t nz = __ballot_sync(0xffffffffu, n0 || n1);
+            act0 = act1 = (nz & L.grp_mask) != 0u;
+          }
+          if (act0) cv[0] = mul_add_rn(cv[0], rc.m, av[0]);
+          if (act1) cv[V - 1] = mul_add_rn(cv[V - 1], rc.m, av[V - 1]);
+        }
+        S.dirty = true;
+      }
+    }
+  }
+}
+
+template <int V>
+__device__ __forceinline__ FusedLane fused_lane(const TargetArgs& A, int cb, int lane) {
+  FusedLane L;
+  const int64_t d0 = (static_cast<int64_t>(cb) * 32 + lane) * V;  // first direction of this lane; rows are padded to K
+  L.gcol = A.g + d0;
+  L.ract = A.rowact + cb;
+  L.K = A.K;
+  L.ncb = A.flag_pitch;
+  L.lane = lane;
+  L.ok0 = d0 < A.n_dirs;
+  L.ok1 = d0 + 1 < A.n_dirs;
+  // the reference's P-lane block of my direction(s): with V = 2 and P >= 2 a block is P/2 lanes
+  const uint32_t P = static_cast<uint32_t>(A.ref_block);
+  const uint32_t lanes_per_grp = (V == 2) ? (P >= 2 ? P / 2 : 1) : P;
+  L.grp_mask = (lanes_per_grp >= 32 ? 0xffffffffu : ((1u << lanes_per_grp) - 1u)) << ((lane / lanes_per_grp) * lanes_per_grp);
+  L.per_component = (V == 2 && P == 1);
+  return L;
+}
+
+// Single-piece fast path, one column block: the warp walks only the heads and the ACTIVE operations of the
+// chunk, found by bit-scanning warp-uniform masks (32 records per mask word), eight row loads in flight.
+// LP: how the reference's P-lane skip rule (adept/jacobian.cpp:392-407) maps to lanes holding V = 2 directions:
+//   0  P = 1: per component;  1  P = 2: the lane's own pair;  2  P >= 4: P/2 adjacent lanes (warp ballot).
+template <int V, int LP>
+__device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
+                                           const uint32_t* __restrict__ headm, const FusedLane& L) {
+  LaneVec<V> acc;
+  acc.zero();
+  // rows are addressed as base + row * (bytes per row): one 32x32->64-bit multiply-add per access
+  char* const gbase = reinterpret_cast<char*>(L.gcol);
+  const uint32_t Kb = static_cast<uint32_t>(L.K) * 8u;
+  uint32_t cur = 0u;
+  bool dirty = false;
+  const int nblk = (n + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int i0 = blk << 5;
+    const uint32_t act = __ballot_sync(0xffffffffu, i0 + L.lane < n && pfw[i0 + L.lane] != 0);
+    const uint32_t hm = headm[blk];
+    uint32_t work = act | hm;
+    const Rec* rb = r + i0;
+    while (work) {
+      int idx[kBatch];
+      LaneVec<V> v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const bool has = work != 0u;
+        const int b = has ? __ffs(work) - 1 : 0;
+        idx[u] = has ? b : -1;
+        work &= work - 1u;   // 0 stays 0
+        v[u].zero();
+        if (has && ((act >> b) & 1u))
+          v[u].load(reinterpret_cast<const double*>(gbase + static_cast<uint64_t>(static_cast<uint32_t>(rb[b].slot)) * Kb));
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (idx[u] < 0) break;
+        if ((hm >> idx[u]) & 1u) {   // next target: retire the previous one
+          if (dirty) {
+            acc.store(reinterpret_cast<double*>(gbase + static_cast<uint64_t>(cur) * Kb));
+            if (L.lane == 0) L.ract[static_cast<int64_t>(cur) * L.ncb] = 1;
+            dirty = false;
+          }
+          cur = static_cast<uint32_t>(rb[idx[u]].slot);
+          acc = v[u];     // +0.0 for a ZMARK (never active) and for an inactive live row
+        } else {          // an active contribution
+          const double m = rb[idx[u]].m;   // re-read from shared memory: keeps the batch's registers for data
+          double* av = reinterpret_cast<double*>(&v[u]);
+          double* cv = reinterpret_cast<double*>(&acc);
+          const bool n0 = L.ok0 && av[0] != 0.0, n1 = L.ok1 && av[V - 1] != 0.0;
+          bool act0, act1;
+          if (LP == 0) {
+            act0 = n0;
+            act1 = n1;
+          } else if (LP == 1) {
+            act0 = act1 = n0 || n1;
+          } else {
+            const uint32_t nz = __ballot_sync(0xffffffffu, n0 || n1);
+            act0 = act1 = (nz & L.grp_mask) != 0u;
+          }
+          if (act0) cv[0] = mul_add_rn(cv[0], m, av[0]);
+          if (V == 2 && act1) cv[V - 1] = mul_add_rn(cv[V - 1], m, av[V - 1]);
+          dirty = true;
+        }
+      }
+    }
+  }
+  if (dirty) {
+    acc.store(reinterpret_cast<double*>(gbase + static_cast<uint64_t>(cur) * Kb));
+    if (L.lane == 0) L.ract[static_cast<int64_t>(cur) * L.ncb] = 1;
+  }
+}
+
+constexpr int kPfPitch = kPieceRecs + 4;   // bytes per column block of the activity table (+4: conflict-free columns)
+
+template <int V, int LP>
 __global__ void __launch_bounds__(256, 3) reverse_fused_kernel(TargetArgs A) {
   __shared__ StageRing ring;
-  __shared__ uint8_t pf[kPieceRecs][8];
+  __shared__ __align__(4) uint8_t pf[kFusedCbs * kPfPitch];   // pf[w*kPfPitch + i]: record i, column block cb0 + w
+  __shared__ uint32_t headm[kPieceRecs / 32];
+  __shared__ uint32_t smask;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int64_t c = A.first_chunk + blockIdx.x;
@@ -530,132 +725,111 @@ __global__ void __launch_bounds__(256, 3) reverse_fused_kernel(TargetArgs A) {
   const int64_t n_recs = r1 - r0;
   const Rec* chunk = A.recs + r0;
   const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
-  const int cb0 = A.cb_lo + blockIdx.y * nwarps;
-  const int cb = cb0 + warp;
+  const int cb0 = A.cb_lo + blockIdx.y * A.cbs;
+  const int cbs = min(A.cbs, A.n_colblocks - cb0);   // column blocks of this CTA
   const int ncb = A.flag_pitch;
-  const bool live = cb < A.n_colblocks;
-  const int64_t d0 = (static_cast<int64_t>(cb) * 32 + lane) * V;  // first direction of this lane; rows are padded to K
-  const bool ok0 = d0 < A.n_dirs, ok1 = d0 + 1 < A.n_dirs;
-  double* gcol = A.g + d0;
-  uint8_t* ract = A.rowact + cb;
-  const uint32_t P = static_cast<uint32_t>(A.ref_block);
-  const uint32_t lanes_per_grp = (V == 2) ? (P >= 2 ? P / 2 : 1) : P;
-  const uint32_t grp_mask =
-      (lanes_per_grp >= 32 ? 0xffffffffu : ((1u << lanes_per_grp) - 1u)) << ((lane / lanes_per_grp) * lanes_per_grp);
-  const bool per_component = (V == 2 && P == 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
     mbar_fence_init();
+    smask = 0u;
   }
   __syncthreads();
   pdl_trigger();
+  if (n_pieces == 1) {
+    // ---- the common case: the chunk is one staged piece; warps take the active column blocks in turn ----
+    const int n = static_cast<int>(n_recs);
+    if (threadIdx.x == 0) issue_piece(ring, chunk, n_recs, 0);
+    pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
+    mbar_wait(&ring.full[0], 0u);
+    const Rec* r = &ring.buf[0][0];
+    // head mask of every block of 32 records
+    for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
+      const int32_t kind = i < n ? r[i].kind : REC_OP;
+      const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
+      if (lane == 0) headm[i >> 5] = h;
+    }
+    // activity bytes: thread t -> record t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
+    uint32_t seen = 0u;   // column blocks for which this thread saw an active contribution
+    for (int t = threadIdx.x; t < n * cbs; t += blockDim.x) {
+      const int i = t / cbs, w = t - i * cbs;
+      const int32_t row = r[i].slot;
+      const int32_t kind = r[i].kind;
+      uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
+      uint8_t f = 0;
+      if (kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
+      else f = *b;
+      pf[w * kPfPitch + i] = f;
+      if (kind == REC_OP && f) seen |= 1u << w;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
+    if (lane == 0 && seen) atomicOr(&smask, seen);
+    __syncthreads();
+    const uint32_t mask = smask;
+    int k = 0;
+    for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
+      if (k % nwarps != warp) continue;
+      const int w = __ffs(mm) - 1;
+      const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
+      fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, L);
+    }
+    return;
+  }
+  // ---- a chunk longer than one piece (a target group of more than kPieceRecs contributions): the chunk is
+  // streamed once per set of nwarps column blocks, warp w bound to one column block, state carried across pieces
+  const int n_sets = (cbs + nwarps - 1) / nwarps;
+  const int64_t total = n_pieces * n_sets;
   if (threadIdx.x == 0)
-    for (int64_t p = 0; p < n_pieces && p < kStages; ++p) issue_piece(ring, chunk, n_recs, p);
-  pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
-
-  LaneVec<V> acc;
-  acc.zero();
-  int32_t cur = -1;        // row whose sum is (or will be) in acc
-  bool cur_zero = false;   // the open group began with a ZMARK (its sum starts from +0.0)
-  bool acc_valid = false;  // acc holds the start value of cur (+ contributions)
-  bool dirty = false;      // acc differs from what memory holds
-  for (int64_t p = 0; p < n_pieces; ++p) {
-    const int st = static_cast<int>(p % kStages);
-    mbar_wait(&ring.full[st], static_cast<uint32_t>((p / kStages) & 1));
+    for (int64_t it = 0; it < total && it < kStages; ++it) issue_piece(ring, chunk, n_recs, it % n_pieces, it);
+  pdl_wait();
+  FusedState<V> S;
+  S.reset();
+  for (int64_t it = 0; it < total; ++it) {
+    const int64_t p = it % n_pieces;
+    const int set = static_cast<int>(it / n_pieces);
+    const int w = set * nwarps + warp;
+    const bool live = w < cbs;
+    const FusedLane L = fused_lane<V>(A, cb0 + (live ? w : 0), lane);
+    if (p == 0) S.reset();
+    const int st = static_cast<int>(it % kStages);
+    mbar_wait(&ring.full[st], static_cast<uint32_t>((it / kStages) & 1));
     const int64_t left = n_recs - p * kPieceRecs;
     const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
     const Rec* r = &ring.buf[st][0];
-    // 1. activity bytes of the piece: thread t -> record t / nwarps, column block cb0 + t % nwarps
     for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
-      const int i = t / nwarps, w = t - i * nwarps;
-      const int32_t row = r[i].slot;
+      const int i = t / nwarps, ww = t - i * nwarps;
       uint8_t f = 0;
-      if (cb0 + w < A.n_colblocks && row >= 0) {
-        uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
-        if (r[i].kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
+      if (set * nwarps + ww < cbs) {
+        uint8_t* b = A.rowact + static_cast<int64_t>(r[i].slot) * ncb + cb0 + set * nwarps + ww;
+        if (r[i].kind == REC_ZMARK) *b = 0;
         else f = *b;
       }
-      pf[i][w] = f;
+      pf[ww * kPfPitch + i] = f;
     }
     __syncthreads();
     if (live) {
       bool mine = false;
-      for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[i][warp] != 0);
+      for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[warp * kPfPitch + i] != 0);
       if (!__any_sync(0xffffffffu, mine)) {
         // nothing to add: retire the open target; remember the last head for a group that goes on
-        if (dirty) {
-          acc.store(gcol + static_cast<int64_t>(cur) * A.K);
-          if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
-          dirty = false;
-        }
+        fused_retire<V>(S, L);
         int last = -1;
         for (int i = lane; i < n; i += 32)
           if (r[i].kind != REC_OP) last = i;
         last = __reduce_max_sync(0xffffffffu, last);
         if (last >= 0) {
-          cur = r[last].slot;
-          cur_zero = (r[last].kind == REC_ZMARK);
-          acc_valid = false;
+          S.cur = r[last].slot;
+          S.cur_zero = (r[last].kind == REC_ZMARK);
+          S.acc_valid = false;
         }
       } else {
-        for (int i = 0; i < n; i += kBatch) {
-          LaneVec<V> v[kBatch];
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            v[u].zero();
-            if (i + u < n && pf[i + u][warp]) v[u].load(gcol + static_cast<int64_t>(r[i + u].slot) * A.K);
-          }
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            if (i + u >= n) break;
-            const Rec rc = r[i + u];
-            if (rc.kind != REC_OP) {  // next target: retire the previous one
-              if (dirty) {
-                acc.store(gcol + static_cast<int64_t>(cur) * A.K);
-                if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
-              }
-              cur = rc.slot;
-              cur_zero = (rc.kind == REC_ZMARK);
-              acc = v[u];  // +0.0 for a ZMARK and for an inactive live row
-              acc_valid = true;
-              dirty = false;
-            } else if (pf[i + u][warp]) {
-              if (!acc_valid) {  // the group began in a piece this warp skipped
-                acc.zero();
-                if (!cur_zero && ract[static_cast<int64_t>(cur) * ncb]) acc.load(gcol + static_cast<int64_t>(cur) * A.K);
-                acc_valid = true;
-              }
-              if (V == 1) {
-                const uint32_t nz = __ballot_sync(0xffffffffu, ok0 && v[u].x != 0.0);
-                if ((nz & grp_mask) != 0u) acc.x = mul_add_rn(acc.x, rc.m, v[u].x);
-              } else {
-                double* av = reinterpret_cast<double*>(&v[u]);
-                double* cv = reinterpret_cast<double*>(&acc);
-                const bool n0 = ok0 && av[0] != 0.0, n1 = ok1 && av[V - 1] != 0.0;
-                bool act0, act1;
-                if (per_component) {
-                  act0 = n0;
-                  act1 = n1;
-                } else {
-                  const uint32_t nz = __ballot_sync(0xffffffffu, n0 || n1);
-                  act0 = act1 = (nz & grp_mask) != 0u;
-                }
-                if (act0) cv[0] = mul_add_rn(cv[0], rc.m, av[0]);
-                if (act1) cv[V - 1] = mul_add_rn(cv[V - 1], rc.m, av[V - 1]);
-              }
-              dirty = true;
-            }
-          }
-        }
+        fused_piece<V>(r, n, &pf[warp * kPfPitch], S, L);
       }
+      if (p == n_pieces - 1) fused_retire<V>(S, L);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
-  }
-  if (live && dirty) {
-    acc.store(gcol + static_cast<int64_t>(cur) * A.K);
-    if (lane == 0) ract[static_cast<int64_t>(cur) * ncb] = 1;
+    if (threadIdx.x == 0 && it + kStages < total) issue_piece(ring, chunk, n_recs, (it + kStages) % n_pieces, it + kStages);
   }
 }
 

@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--fused", type=int, default=1, help="reverse level sweep as one kernel per step (0: snapshot + gather)")
+    ap.add_argument("--cbs", type=int, default=0, help="fused kernel: column blocks per CTA (0 = automatic)")
     args = ap.parse_args()
     if args.workload in ("rosenbrock1e7", "ensemble1e5"):
         return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
@@ -339,6 +340,7 @@ def main():
     eng.set_option("persistent", args.persistent)
     eng.set_option("chunk_recs", args.chunk)
     eng.set_option("fused", args.fused)
+    eng.set_option("cbs", args.cbs)
     if args.streams:
         eng.set_option("streams", args.streams)
 
@@ -409,6 +411,7 @@ def main():
     eng.set_option("time_kernels", 1)
     step()
     dom_ms, dom_launches = eng.stat("dominant_ms", 0.0), eng.stat("dominant_launches", 0.0)
+    dom_quarters = [eng.stat(f"dominant_q{q}_ms", None) for q in (1, 2, 3, 4)]
     sweep_ms = eng.stat("sweep_ms", 0.0)
     used = eng.stat("used_schedule", 0.0)
     used_fused = bool(eng.stat("used_fused", 0.0)) and used == 2 and mode == 1
@@ -484,6 +487,7 @@ def main():
                 "peak_source": peak_src, "launches_per_step": dom_launches,
                 "algorithmic_bytes_per_launch": dom_bytes / dom_launches,
                 "avg_launch_us": 1e3 * dom_ms / dom_launches,
+                "ms_by_quarter_of_sweep": dom_quarters,
                 "whole_sweep_frac": (bpo * work / world) / (sweep_ms / 1e3) / 1e9 / peak if sweep_ms else None,
                 "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
                         "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}

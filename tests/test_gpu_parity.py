@@ -85,6 +85,38 @@ def test_reverse_level_sweep_per_step_and_persistent(engine, name, persistent):
         engine.set_option("pass_dirs", 0)
 
 
+def broadcast_tape(n=700, fan=64, seed=1):
+    """x0, x1 feed EVERY statement of a layer (y_i = a_i x0 + b_i x1), and a second layer mixes the y's:
+    in the reverse sweep x0 and x1 each receive n contributions within one step -- one target group of more
+    than 256 records, i.e. a chunk the kernels must stream in several pieces."""
+    rng = np.random.default_rng(seed)
+    stmt, mult, idx = [[-1, 0]], [], []
+    for i in range(n):                                   # slots 2 .. n+1
+        idx += [0, 1]; mult += list(rng.uniform(-1, 1, 2))
+        stmt.append([2 + i, len(idx)])
+    for k in range(n):                                   # slots n+2 .. 2n+1
+        src = rng.choice(n, fan, replace=False)
+        idx += list(2 + src); mult += list(rng.uniform(-1, 1, fan))
+        stmt.append([2 + n + k, len(idx)])
+    return dict(stmt=np.array(stmt, np.int32), mult=np.array(mult), idx=np.array(idx, np.int32), max_gradient=2 * n + 2,
+                indep=np.array([0, 1], np.int32), dep=np.arange(2 + n, 2 + 2 * n, dtype=np.int32))
+
+
+@pytest.mark.parametrize("cbs", [0, 32, 3])
+def test_target_groups_longer_than_a_staged_piece(engine, po, cbs):
+    t = broadcast_tape()
+    try:
+        for schedule in (LEVELS, UNFUSED, ORDERED):
+            upload(engine, t, schedule)
+            engine.set_option("cbs", cbs)                # fused kernel: column blocks per CTA (32 > 8 warps: two sets)
+            check_jacobians(engine, po, t, f"broadcast schedule {schedule} cbs {cbs}")
+            g0 = np.zeros(t["max_gradient"]); g0[t["dep"]] = np.linspace(-1, 1, t["dep"].size)
+            flags = 0 if schedule != ORDERED else 1
+            assert same_bits(engine.adjoint(g0, True, flags), po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
+    finally:
+        engine.set_option("cbs", 0)
+
+
 # ---- the device-side dependency analysis ------------------------------------------------------------
 @pytest.mark.parametrize("window", [0, 64, 777, 4096])
 def test_levels_match_the_sequential_rule(engine, po, pkg, window):

@@ -1,0 +1,23 @@
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/t2_pytest.log 2>&1
+tail -4 gpurun_out/t2_pytest.log
+run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --e2e-steps 0 "$@" > gpurun_out/t2_$name.json 2> gpurun_out/t2_$name.err; python - gpurun_out/t2_$name.json $name <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1])); r=d.get('roofline') or {}
+    print(sys.argv[2], 'ms', round(d['ms_per_step'],1), 'parity', d.get('parity_bit_exact_vs_oracle'), 'launch_us', round(r.get('avg_launch_us',0),1), 'frac', round(r.get('frac',0),2), 'launches', d.get('gpu_launches'))
+except Exception as e:
+    print(sys.argv[2], 'FAILED', e)
+PY
+}
+run toon_auto
+run toon_c32_s1 --cbs 32 --streams 1
+run toon_c32_s2 --cbs 32 --streams 2
+run toon_c16_s4 --cbs 16 --streams 4
+run toon_c16_s4_w4 --cbs 16 --streams 4 --warps 4
+run toon_c8_s4 --cbs 8 --streams 4
+run toon_c8_s8 --cbs 8 --streams 8
+run toon_c32_s2_k128 --cbs 32 --streams 2 --chunk 128
+run toon_c16_s4_k32 --cbs 16 --streams 4 --chunk 32
+run syn_auto --workload synthetic1e7_rev
+run syn_c16 --workload synthetic1e7_rev --cbs 16
