@@ -643,50 +643,77 @@ __device__ __forceinline__ FusedLane fused_lane(const TargetArgs& A, int cb, int
 //   0  P = 1: per component;  1  P = 2: the lane's own pair;  2  P >= 4: P/2 adjacent lanes (warp ballot).
 template <int V, int LP>
 __device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
-                                           const uint32_t* __restrict__ headm, const FusedLane& L) {
+                                           const uint32_t* __restrict__ headm, uint4* __restrict__ wl,
+                                           const FusedLane& L) {
+  // Per block of 32 records the lanes decode ONE record each (row byte offset = row * bytes per row, flags) and
+  // park the heads and the active operations, compacted and in order, in the warp's list wl[]:
+  //   x = low word of the byte offset | 1 (head) | 2 (row is active: load it), y = high word,
+  //   (z, w) = multiplier bits (operation) or z = row (head)
+  // so that the serial walk below costs one 16-byte shared-memory read and one 64-bit add per record.
   LaneVec<V> acc;
   acc.zero();
-  // rows are addressed as base + row * (bytes per row): one 32x32->64-bit multiply-add per access
   char* const gbase = reinterpret_cast<char*>(L.gcol);
-  const uint32_t Kb = static_cast<uint32_t>(L.K) * 8u;
-  uint32_t cur = 0u;
+  const uint32_t Kb = static_cast<uint32_t>(L.K) * 8u;   // bytes per row: a multiple of 512, the low bits are free
+  uint64_t cur_off = 0;
+  uint32_t cur_row = 0u;
   bool dirty = false;
+  const uint32_t lt_mask = (1u << L.lane) - 1u;
   const int nblk = (n + 31) >> 5;
   for (int blk = 0; blk < nblk; ++blk) {
-    const int i0 = blk << 5;
-    const uint32_t act = __ballot_sync(0xffffffffu, i0 + L.lane < n && pfw[i0 + L.lane] != 0);
+    const int i = (blk << 5) + L.lane;
+    const bool valid = i < n;
+    const bool a = valid && pfw[i] != 0;
+    const uint32_t act = __ballot_sync(0xffffffffu, a);
     const uint32_t hm = headm[blk];
-    uint32_t work = act | hm;
-    const Rec* rb = r + i0;
-    while (work) {
-      int idx[kBatch];
+    const uint32_t work = act | hm;
+    if (work == 0u) continue;
+    if ((work >> L.lane) & 1u) {
+      const Rec rc = r[i];
+      const bool head = (hm >> L.lane) & 1u;
+      const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(rc.slot)) * Kb;
+      uint4 e;
+      e.x = static_cast<uint32_t>(off) | (head ? 1u : 0u) | (a ? 2u : 0u);
+      e.y = static_cast<uint32_t>(off >> 32);
+      const uint64_t mb = static_cast<uint64_t>(__double_as_longlong(rc.m));
+      e.z = head ? static_cast<uint32_t>(rc.slot) : static_cast<uint32_t>(mb);
+      e.w = static_cast<uint32_t>(mb >> 32);
+      wl[__popc(work & lt_mask)] = e;
+    }
+    __syncwarp();
+    const int cnt = __popc(work);
+    for (int j = 0; j < cnt; j += kBatch) {
       LaneVec<V> v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const bool has = work != 0u;
-        const int b = has ? __ffs(work) - 1 : 0;
-        idx[u] = has ? b : -1;
-        work &= work - 1u;   // 0 stays 0
         v[u].zero();
-        if (has && ((act >> b) & 1u))
-          v[u].load(reinterpret_cast<const double*>(gbase + static_cast<uint64_t>(static_cast<uint32_t>(rb[b].slot)) * Kb));
+        if (j + u < cnt) {
+          const uint2 e = *reinterpret_cast<const uint2*>(&wl[j + u]);
+          if (e.x & 2u)
+            v[u].load(reinterpret_cast<const double*>(gbase + ((static_cast<uint64_t>(e.y) << 32) | (e.x & ~15u))));
+        }
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        if (idx[u] < 0) break;
-        if ((hm >> idx[u]) & 1u) {   // next target: retire the previous one
+        if (j + u >= cnt) break;
+        const uint4 e = wl[j + u];
+        if (e.x & 1u) {   // next target: retire the previous one
           if (dirty) {
-            acc.store(reinterpret_cast<double*>(gbase + static_cast<uint64_t>(cur) * Kb));
-            if (L.lane == 0) L.ract[static_cast<int64_t>(cur) * L.ncb] = 1;
+            if (!L.ok0) acc.zero();   // lanes beyond the last direction stay +0.0 in memory (see below)
+            if (V == 2 && !L.ok1) reinterpret_cast<double*>(&acc)[V - 1] = 0.0;
+            acc.store(reinterpret_cast<double*>(gbase + cur_off));
+            if (L.lane == 0) L.ract[static_cast<int64_t>(cur_row) * L.ncb] = 1;
             dirty = false;
           }
-          cur = static_cast<uint32_t>(rb[idx[u]].slot);
+          cur_off = (static_cast<uint64_t>(e.y) << 32) | (e.x & ~15u);
+          cur_row = e.z;
           acc = v[u];     // +0.0 for a ZMARK (never active) and for an inactive live row
         } else {          // an active contribution
-          const double m = rb[idx[u]].m;   // re-read from shared memory: keeps the batch's registers for data
+          const double m = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(e.w) << 32) | e.z));
           double* av = reinterpret_cast<double*>(&v[u]);
           double* cv = reinterpret_cast<double*>(&acc);
-          const bool n0 = L.ok0 && av[0] != 0.0, n1 = L.ok1 && av[V - 1] != 0.0;
+          // padded lanes (direction >= n_dirs) always read +0.0: they are never seeded and are masked at every
+          // store, so they cannot wake a reference block even when a non-finite multiplier makes them NaN
+          const bool n0 = av[0] != 0.0, n1 = av[V - 1] != 0.0;
           bool act0, act1;
           if (LP == 0) {
             act0 = n0;
@@ -703,20 +730,24 @@ __device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, con
         }
       }
     }
+    __syncwarp();   // the list is rewritten for the next block
   }
   if (dirty) {
-    acc.store(reinterpret_cast<double*>(gbase + static_cast<uint64_t>(cur) * Kb));
-    if (L.lane == 0) L.ract[static_cast<int64_t>(cur) * L.ncb] = 1;
+    if (!L.ok0) acc.zero();
+    if (V == 2 && !L.ok1) reinterpret_cast<double*>(&acc)[V - 1] = 0.0;
+    acc.store(reinterpret_cast<double*>(gbase + cur_off));
+    if (L.lane == 0) L.ract[static_cast<int64_t>(cur_row) * L.ncb] = 1;
   }
 }
 
 constexpr int kPfPitch = kPieceRecs + 4;   // bytes per column block of the activity table (+4: conflict-free columns)
 
 template <int V, int LP>
-__global__ void __launch_bounds__(256, 3) reverse_fused_kernel(TargetArgs A) {
+__global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
   __shared__ StageRing ring;
   __shared__ __align__(4) uint8_t pf[kFusedCbs * kPfPitch];   // pf[w*kPfPitch + i]: record i, column block cb0 + w
   __shared__ uint32_t headm[kPieceRecs / 32];
+  __shared__ uint4 wlist[8][32];   // per warp: the decoded heads and active operations of a block of 32 records
   __shared__ uint32_t smask;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -772,7 +803,7 @@ __global__ void __launch_bounds__(256, 3) reverse_fused_kernel(TargetArgs A) {
       if (k % nwarps != warp) continue;
       const int w = __ffs(mm) - 1;
       const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
-      fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, L);
+      fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, &wlist[warp][0], L);
     }
     return;
   }

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/t6_pytest.log 2>&1
-tail -4 gpurun_out/t6_pytest.log
-run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --e2e-steps 0 "$@" > gpurun_out/t6_$name.json 2> gpurun_out/t6_$name.err; python - gpurun_out/t6_$name.json $name <<'PY'
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/t7_pytest.log 2>&1
+tail -4 gpurun_out/t7_pytest.log
+run() { name=$1; shift; timeout 300 python bench.py --no-cpu-baseline --e2e-steps 0 "$@" > gpurun_out/t7_$name.json 2> gpurun_out/t7_$name.err; python - gpurun_out/t7_$name.json $name <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); r=d.get('roofline') or {}
@@ -16,4 +16,4 @@ run toon_c8_s4 --cbs 8 --streams 4
 run toon_k128 --chunk 128
 run toon_unfused --fused 0
 run syn_auto --workload synthetic1e7_rev
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:reverse_fused -s 2803 -c 1 -o gpurun_out/t6_ncu_toon_s2802 -f python bench.py --no-cpu-baseline --e2e-steps 0 --steps 1 --warmup 0 --streams 1 > gpurun_out/t6_ncu_2802.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:reverse_fused -s 2803 -c 1 -o gpurun_out/t7_ncu_toon_s2802 -f python bench.py --no-cpu-baseline --e2e-steps 0 --steps 1 --warmup 0 --streams 1 > gpurun_out/t7_ncu_2802.log 2>&1
