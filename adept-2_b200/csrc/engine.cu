@@ -390,8 +390,9 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   RET(ensure(errp, cap, size_t(n_windows + 1) * 8));
   RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
   // small gradient lists: direct-indexed table in shared memory, dense per-window state for the packing pass
-  const size_t dense_smem = size_t(s.max_gradient) * 8;
-  const bool dense = dense_smem <= (size_t(160) << 10) && size_t(n_windows) * dense_smem <= (size_t(2) << 30);
+  const size_t dense_tab = size_t(s.max_gradient) * 8;
+  const size_t dense_smem = dense_tab + kWinStageBytes;   // table + cp.async staging of statements and operands
+  const bool dense = dense_tab <= (size_t(160) << 10) && size_t(n_windows) * dense_tab <= (size_t(2) << 30);
   Buf& wstate = s.pool[33];
   RET(ensure(errp, s.level, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wdepth, size_t(n_windows + 1) * 4));
@@ -399,7 +400,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   CK(cudaMemsetAsync(wdepth.p, 0, size_t(n_windows + 1) * 4, s.stream));
   RET(ensure(errp, tab_off, size_t(n_windows + 1) * 8));
   if (dense) {
-    RET(ensure(errp, wstate, size_t(n_windows) * dense_smem));
+    RET(ensure(errp, wstate, size_t(n_windows) * dense_tab));
     CK(cudaFuncSetAttribute(window_levels_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem)));
     window_levels_smem_kernel<<<unsigned(n_windows), 32, dense_smem, s.stream>>>(
         s.stmt.as<int2>(), s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, s.max_gradient, wstate.as<int2>(),

@@ -266,12 +266,35 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
 // array in shared memory instead of a hash table in L2, which takes the L2 round trip out of every
 // statement.  One warp (= one CTA) per window; the window's final table is written to wstate[w][slot]
 // for the packing pass.
+//
+// The walk is a chain of dependent shared-memory round trips (operand -> table entry -> max -> table
+// update), ~150 cycles per statement; a global load inside that chain would cost several times as much.
+// So the window's statements and operands are streamed into shared memory ahead of the walk with
+// cp.async (no registers held): tiles of kWinTile statements, statement tiles two ahead (their ends size
+// the operand copy), operand tiles one ahead.  A tile with more than kWinIdxCap operands (a long
+// statement) reads its operands from global memory instead.
+constexpr int kWinTile = 128;
+constexpr int kWinIdxCap = 4096;
+constexpr size_t kWinStageBytes = size_t(3) * (kWinTile + 1) * sizeof(int2) + size_t(2) * kWinIdxCap * sizeof(int32_t);
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(32) window_levels_smem_kernel(const int2* __restrict__ stmt, const int32_t* __restrict__ idx,
                                                                 const int64_t* __restrict__ win_lo, int64_t n_windows,
                                                                 int64_t max_gradient, int2* __restrict__ wstate,
                                                                 int32_t* __restrict__ level,
                                                                 int32_t* __restrict__ win_depth) {
-  extern __shared__ int2 tab[];   // tab[slot] = {writer step, max reader step}; 0 = none
+  extern __shared__ int2 tab[];   // tab[slot] = {writer step, max reader step}; 0 = none; then the staging buffers
+  int2* const sbuf = tab + max_gradient;                                        // [3][kWinTile + 1]
+  int32_t* const ibuf = reinterpret_cast<int32_t*>(sbuf + 3 * (kWinTile + 1));  // [2][kWinIdxCap]
   const int64_t w = blockIdx.x;
   const int lane = threadIdx.x;
   if (w >= n_windows) return;
@@ -286,59 +309,99 @@ __global__ void __launch_bounds__(32) window_levels_smem_kernel(const int2* __re
     return;
   }
   for (int64_t i = lane; i < max_gradient; i += 32) tab[i] = make_int2(0, 0);
-  __syncwarp();
-  int32_t depth = 0;
-  int64_t o0 = stmt[lo - 1].y;
-  int2 st = stmt[lo];
-  int2 st_next = (lo < hi) ? stmt[lo + 1] : st;
-  int32_t x_pre = (o0 + lane < st.y) ? idx[o0 + lane] : -1;   // operand of the current statement for this lane
-  for (int64_t s = lo; s <= hi; ++s) {
-    const int64_t o1 = st.y;
-    const int32_t lhs = st.x;
-    const int64_t nops = o1 - o0;
-    // prefetch: statement s+2 and the first 32 operands of statement s+1 (independent of the table work)
-    const int2 st_next2 = (s + 1 < hi) ? stmt[s + 2] : st_next;
-    const int32_t x_next = (s < hi && o1 + lane < st_next.y) ? idx[o1 + lane] : -1;
-    int32_t lv = 1;
-    if (nops < 32) {
-      const int32_t x = (lane < nops) ? x_pre : (lane == nops ? lhs : -1);
-      if (x >= 0) {
-        const int2 e = tab[x];
-        lv = (lane < nops) ? max(e.x + 1, e.y) : max(e.x, e.y) + 1;
-        lv = max(lv, 1);
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-      if (lane < nops) tab[x].y = lv;
-      __syncwarp();
-      if (lane == nops) {
-        tab[x] = make_int2(lv, 0);
-        level[s] = lv;
-      }
-    } else {
-      for (int64_t o = o0 + lane; o < o1; o += 32) {
-        const int2 e = tab[idx[o]];
-        lv = max(lv, max(e.x + 1, e.y));
-      }
-      const int2 eL = tab[lhs];
-      lv = max(lv, max(eL.x, eL.y) + 1);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-      __syncwarp();
-      for (int64_t o = o0 + lane; o < o1; o += 32) tab[idx[o]].y = lv;
-      __syncwarp();
-      if (lane == 0) {
-        tab[lhs] = make_int2(lv, 0);
-        level[s] = lv;
+  const int64_t n_tiles = (hi - lo + 1 + kWinTile - 1) / kWinTile;
+  // statement tile t -> sbuf[t % 3][0 .. cnt]: entry 0 is the statement BEFORE the tile (its end = first operand)
+  auto issue_stmts = [&](int64_t t) {
+    if (t < n_tiles) {
+      const int64_t s0 = lo + t * kWinTile;
+      const int cnt = static_cast<int>(min(static_cast<int64_t>(kWinTile), hi + 1 - s0));
+      int2* dst = sbuf + (t % 3) * (kWinTile + 1);
+      for (int k = lane; k <= cnt; k += 32) cp_async8(dst + k, stmt + s0 - 1 + k);
+    }
+    cp_async_commit();
+  };
+  // operand tile t -> ibuf[t % 2] (statement tile t must have arrived)
+  auto issue_ops = [&](int64_t t) {
+    if (t < n_tiles) {
+      const int64_t s0 = lo + t * kWinTile;
+      const int cnt = static_cast<int>(min(static_cast<int64_t>(kWinTile), hi + 1 - s0));
+      const int2* sb = sbuf + (t % 3) * (kWinTile + 1);
+      const int64_t o0 = sb[0].y, n = static_cast<int64_t>(sb[cnt].y) - o0;
+      if (n <= kWinIdxCap) {
+        int32_t* dst = ibuf + (t % 2) * kWinIdxCap;
+        for (int64_t k = lane; k < n; k += 32) cp_async4(dst + k, idx + o0 + k);
       }
     }
+    cp_async_commit();
+  };
+  issue_stmts(0);
+  issue_stmts(1);
+  cp_async_wait<1>();
+  __syncwarp();
+  issue_ops(0);
+  int32_t depth = 0;
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    issue_stmts(t + 2);   // pending, oldest first: S(t+1), I(t), S(t+2)
+    cp_async_wait<2>();   // S(t+1) has arrived
     __syncwarp();
-    depth = max(depth, lv);
-    o0 = o1;
-    st = st_next;
-    st_next = st_next2;
-    x_pre = x_next;
+    issue_ops(t + 1);     // pending: I(t), S(t+2), I(t+1)
+    cp_async_wait<2>();   // I(t) has arrived
+    __syncwarp();
+    const int64_t s0 = lo + t * kWinTile;
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(kWinTile), hi + 1 - s0));
+    const int2* sb = sbuf + (t % 3) * (kWinTile + 1);
+    const int64_t tile_o0 = sb[0].y;
+    const bool staged = static_cast<int64_t>(sb[cnt].y) - tile_o0 <= kWinIdxCap;
+    const int32_t* ib = ibuf + (t % 2) * kWinIdxCap;
+    int64_t o0 = tile_o0;
+    const int tile_lo32 = static_cast<int>(tile_o0);   // ends of a staged tile are compared in 32 bits (wrap-safe)
+    int o0r = 0;          // o0 - tile_o0
+    int32_t mylv = 0;     // lane (k-1) & 31 keeps the step of statement k: one coalesced store per 32 statements
+    for (int k = 1; k <= cnt; ++k) {
+      const int2 st = sb[k];
+      const int o1r = st.y - tile_lo32;
+      const int nops = o1r - o0r;
+      int32_t lv = 1;
+      if (staged && nops < 32) {
+        // the common case, kept to ~30 instructions: a single warp walks the window, so every instruction of this
+        // dependent chain is paid in full
+        const int32_t lhs = st.x;
+        const int32_t x = (lane < nops) ? ib[o0r + lane] : lhs;
+        const int2 e = tab[x];
+        int32_t v = (lane < nops) ? max(e.x + 1, e.y)    // RAW (strict), MONO (non-strict)
+                                  : max(e.x, e.y) + 1;   // WAW, WAR (strict)
+        v = (lane <= nops) ? max(v, 1) : 1;
+        lv = __reduce_max_sync(0xffffffffu, v);
+        if (lane < nops && x != lhs) tab[x].y = lv;      // readers of the live version (a self reference is retired below)
+        if (lane == nops) tab[lhs] = make_int2(lv, 0);   // the write retires the old version and its readers
+      } else {
+        const int32_t lhs = st.x;
+        const int64_t o1 = o0 + nops;
+        for (int64_t o = o0 + lane; o < o1; o += 32) {
+          const int2 e = tab[staged ? ib[o - tile_o0] : idx[o]];
+          lv = max(lv, max(e.x + 1, e.y));
+        }
+        const int2 eL = tab[lhs];
+        lv = max(lv, max(eL.x, eL.y) + 1);
+        lv = __reduce_max_sync(0xffffffffu, lv);
+        __syncwarp();
+        for (int64_t o = o0 + lane; o < o1; o += 32) tab[staged ? ib[o - tile_o0] : idx[o]].y = lv;
+        __syncwarp();
+        if (lane == 0) tab[lhs] = make_int2(lv, 0);
+      }
+      __syncwarp();
+      if (lane == ((k - 1) & 31)) mylv = lv;
+      if ((k & 31) == 0 || k == cnt) {
+        const int kb = (k - 1) & ~31;   // statements kb+1 .. k of the tile
+        if (kb + lane < k) level[s0 + kb + lane] = mylv;
+      }
+      depth = max(depth, lv);
+      o0 += nops;
+      o0r = o1r;
+    }
+    __syncwarp();   // the buffers of tile t are rewritten two and three tiles from now
   }
+  cp_async_wait<0>();
   for (int64_t i = lane; i < max_gradient; i += 32) out[i] = tab[i];
   if (lane == 0) win_depth[w] = depth;
 }

@@ -424,6 +424,7 @@ def main():
     if args.e2e_steps > 0:
         t0 = time.perf_counter()
         t_up = t_jac = 0.0
+        each = []
         for _ in range(args.e2e_steps):
             ta = time.perf_counter()
             upload()
@@ -432,8 +433,11 @@ def main():
                 eng.jacobian(mode, indep, dep, out=out_pin.numpy())
             else:
                 eng.jacobian_device(mode, indep, dep, 0)
+            tc = time.perf_counter()
             t_up += tb - ta
-            t_jac += time.perf_counter() - tb
+            t_jac += tc - tb
+            each.append([round(1e3 * (tb - ta), 2), round(1e3 * (tc - tb), 2), round(eng.stat("replay_ms", 0.0), 2)])
+        phases["each_step_upload_jacobian_replay_ms"] = each
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
         phases["upload_call_ms"] = 1e3 * t_up / args.e2e_steps
