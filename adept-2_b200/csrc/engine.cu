@@ -41,6 +41,7 @@ constexpr int64_t kMaxStepWidth = int64_t(1) << 20;   // statements per step (wi
 constexpr double kWideStepCtas = 4096.0;              // average CTAs per step above which one CUDA stream suffices
 constexpr size_t kStageBytes = size_t(32) << 20;      // pinned staging buffer for pageable uploads (two of them)
 constexpr size_t kPoolKeepBytes = size_t(8) << 30;    // analysis temporaries kept between uploads up to this size
+constexpr int64_t kTailItems = 4;                     // (chunks x column groups) up to which a step rides along as a tail
 constexpr size_t kPoolSlots = 48;                     // analysis temporaries (Shard::pool)
 
 struct Buf {
@@ -82,7 +83,7 @@ struct Shard {
   bool have_target = false;
   // fused reverse stream (versioned rows, one kernel per step; built on first need)
   bool have_fused = false;
-  Buf ftgt, fchunk, fpar, out_rows;
+  Buf ftgt, fchunk, fpar, out_rows, done;
   int64_t n_fchunks = 0, R_f = 0, chunk_recs = 0;
   std::vector<int64_t> step_fchunk;   // [n_levels+2] first fused chunk of each step
   Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
@@ -128,6 +129,7 @@ struct adept_cuda_ctx {
   int opt_smallg = 1;   // use the shared-memory-resident kernel when the gradient list fits
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
+  int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -988,7 +990,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     // per step snapshot a_s and zero the LHS slots, then gather per target.
     constexpr int V = 2;   // a lane owns two adjacent directions: 16-byte row accesses
     if (!fused) RET(ensure_target_stream(c, s));
-    TargetArgs B;
+    TargetArgs B{};
     B.recs = (fused ? s.ftgt : s.tgt).as<Rec>();
     B.chunk_begin = (fused ? s.fchunk : s.tchunk).as<int64_t>();
     B.g = g;
@@ -1056,6 +1058,11 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       s.aux.push_back(st);
       s.aux_ev.push_back(ev);
     }
+    if (fused && c->opt_tail) {  // ticket counters of the launches that carry tail steps
+      const size_t nb = size_t(nstr) * size_t(s.n_levels + 1) * sizeof(unsigned int);
+      RET(ensure(errp, s.done, nb));
+      CK(cudaMemsetAsync(s.done.p, 0, nb, s.stream));
+    }
     if (nstr > 1) {
       CK(cudaEventRecord(s.fork_ev, s.stream));
       for (int i = 1; i < nstr; ++i) CK(cudaStreamWaitEvent(s.aux[i - 1], s.fork_ev, 0));
@@ -1083,6 +1090,19 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
           const int64_t c0 = s.step_fchunk[l], c1 = s.step_fchunk[l + 1];
           if (c1 <= c0) continue;
           Bi.first_chunk = c0;
+          // steps of a chunk or two that follow ride along with this launch (run by its last CTA)
+          Bi.n_tail = 0;
+          while (c->opt_tail && Bi.n_tail < kMaxTail && l - 1 >= 1) {
+            const int64_t t0 = s.step_fchunk[l - 1], t1 = s.step_fchunk[l];
+            if ((t1 - t0) * int64_t(g_hi - g_lo) > kTailItems) break;
+            if (t1 > t0) {
+              Bi.tail_c0[Bi.n_tail] = t0;
+              Bi.tail_c1[Bi.n_tail] = t1;
+              ++Bi.n_tail;
+            }
+            --l;
+          }
+          Bi.done = Bi.n_tail ? s.done.as<unsigned int>() + size_t(i) * size_t(s.n_levels + 1) + size_t(l) : nullptr;
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           const dim3 fgrid(unsigned(c1 - c0), unsigned(g_hi - g_lo)), fblock(twarps * 32);
           if (B.ref_block == 1) launch_pdl(reverse_fused_kernel<V, 0>, fgrid, fblock, st, pdl, Bi);
@@ -1609,7 +1629,7 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.pos_in_sched, &s.ftgt, &s.fchunk, &s.fpar, &s.out_rows, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.pos_in_sched, &s.ftgt, &s.fchunk, &s.fpar, &s.out_rows, &s.done, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
@@ -2004,6 +2024,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_smallg = value ? 1 : 0;
   } else if (k == "fused") {
     c->opt_fused = value ? 1 : 0;
+  } else if (k == "tail") {
+    c->opt_tail = value ? 1 : 0;
   } else if (k == "cbs") {
     if (value < 0 || value > kFusedCbs) return fail(errp, ADEPT_CUDA_ERR_ARG, "cbs must be in 0..32");
     c->opt_cbs = int(value);

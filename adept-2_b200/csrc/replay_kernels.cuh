@@ -360,7 +360,14 @@ struct TargetArgs {
   int64_t n_dirs;
   int ref_block;
   int cbs;           // reverse_fused_kernel: column blocks per CTA (<= kFusedCbs)
+  // reverse_fused_kernel: "tail" steps.  Steps of a chunk or two (boundary statements between two wide levels, scalar
+  // chains) are not worth a launch of their own: the launch of the step before them carries them along, and the
+  // CTA that finishes last (ticket counter *done) runs them one after the other.
+  int n_tail;
+  int64_t tail_c0[4], tail_c1[4];   // chunk range of every tail step, in sweep order
+  unsigned int* done;
 };
+constexpr int kMaxTail = 4;
 
 // The CTA first fetches, in one round trip and for all its warps, the activity byte of every
 // record of the staged piece (pf); a warp whose column block has no active contribution in the
@@ -560,6 +567,8 @@ struct FusedLane {
 template <int V>
 __device__ __forceinline__ void fused_retire(FusedState<V>& S, const FusedLane& L) {
   if (S.dirty) {
+    if (!L.ok0) S.acc.zero();   // lanes beyond the last direction stay +0.0 in memory (fused_task relies on it)
+    if (V == 2 && !L.ok1) reinterpret_cast<double*>(&S.acc)[V - 1] = 0.0;
     S.acc.store(L.gcol + static_cast<int64_t>(S.cur) * L.K);
     if (L.lane == 0) L.ract[static_cast<int64_t>(S.cur) * L.ncb] = 1;
     S.dirty = false;
@@ -749,118 +758,151 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
   __shared__ uint32_t headm[kPieceRecs / 32];
   __shared__ uint4 wlist[8][32];   // per warp: the decoded heads and active operations of a block of 32 records
   __shared__ uint32_t smask;
+  __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  const int64_t c = A.first_chunk + blockIdx.x;
-  const int64_t r0 = A.chunk_begin[c], r1 = A.chunk_begin[c + 1];
-  const int64_t n_recs = r1 - r0;
-  const Rec* chunk = A.recs + r0;
-  const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
-  const int cb0 = A.cb_lo + blockIdx.y * A.cbs;
-  const int cbs = min(A.cbs, A.n_colblocks - cb0);   // column blocks of this CTA
   const int ncb = A.flag_pitch;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
-    mbar_fence_init();
-    smask = 0u;
-  }
-  __syncthreads();
-  pdl_trigger();
-  if (n_pieces == 1) {
-    // ---- the common case: the chunk is one staged piece; warps take the active column blocks in turn ----
-    const int n = static_cast<int>(n_recs);
-    if (threadIdx.x == 0) issue_piece(ring, chunk, n_recs, 0);
-    pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
-    mbar_wait(&ring.full[0], 0u);
-    const Rec* r = &ring.buf[0][0];
-    // head mask of every block of 32 records
-    for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
-      const int32_t kind = i < n ? r[i].kind : REC_OP;
-      const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
-      if (lane == 0) headm[i >> 5] = h;
+  // work items of this CTA: its own (chunk, column group) and, if it turns out to be the last CTA of a launch
+  // that carries tail steps, every (chunk, column group) of those steps, step after step
+  int64_t c = A.first_chunk + blockIdx.x;
+  int cby = blockIdx.y;
+  int tail = -1;   // -1: own item; >= 0: tail step being run
+  for (;;) {
+    if (threadIdx.x == 0) {
+      if (tail >= 0)
+        for (int s = 0; s < kStages; ++s) mbar_inval(&ring.full[s]);
+      for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
+      mbar_fence_init();
+      smask = 0u;
     }
-    // activity bytes: thread t -> record t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
-    uint32_t seen = 0u;   // column blocks for which this thread saw an active contribution
-    for (int t = threadIdx.x; t < n * cbs; t += blockDim.x) {
-      const int i = t / cbs, w = t - i * cbs;
-      const int32_t row = r[i].slot;
-      const int32_t kind = r[i].kind;
-      uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
-      uint8_t f = 0;
-      if (kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
-      else f = *b;
-      pf[w * kPfPitch + i] = f;
-      if (kind == REC_OP && f) seen |= 1u << w;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
-    if (lane == 0 && seen) atomicOr(&smask, seen);
     __syncthreads();
-    const uint32_t mask = smask;
-    int k = 0;
-    for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
-      if (k % nwarps != warp) continue;
-      const int w = __ffs(mm) - 1;
-      const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
-      fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, &wlist[warp][0], L);
-    }
-    return;
-  }
-  // ---- a chunk longer than one piece (a target group of more than kPieceRecs contributions): the chunk is
-  // streamed once per set of nwarps column blocks, warp w bound to one column block, state carried across pieces
-  const int n_sets = (cbs + nwarps - 1) / nwarps;
-  const int64_t total = n_pieces * n_sets;
-  if (threadIdx.x == 0)
-    for (int64_t it = 0; it < total && it < kStages; ++it) issue_piece(ring, chunk, n_recs, it % n_pieces, it);
-  pdl_wait();
-  FusedState<V> S;
-  S.reset();
-  for (int64_t it = 0; it < total; ++it) {
-    const int64_t p = it % n_pieces;
-    const int set = static_cast<int>(it / n_pieces);
-    const int w = set * nwarps + warp;
-    const bool live = w < cbs;
-    const FusedLane L = fused_lane<V>(A, cb0 + (live ? w : 0), lane);
-    if (p == 0) S.reset();
-    const int st = static_cast<int>(it % kStages);
-    mbar_wait(&ring.full[st], static_cast<uint32_t>((it / kStages) & 1));
-    const int64_t left = n_recs - p * kPieceRecs;
-    const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
-    const Rec* r = &ring.buf[st][0];
-    for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
-      const int i = t / nwarps, ww = t - i * nwarps;
-      uint8_t f = 0;
-      if (set * nwarps + ww < cbs) {
-        uint8_t* b = A.rowact + static_cast<int64_t>(r[i].slot) * ncb + cb0 + set * nwarps + ww;
-        if (r[i].kind == REC_ZMARK) *b = 0;
+    if (tail < 0) pdl_trigger();
+    const int64_t r0 = A.chunk_begin[c], r1 = A.chunk_begin[c + 1];
+    const int64_t n_recs = r1 - r0;
+    const Rec* chunk = A.recs + r0;
+    const int64_t n_pieces = (n_recs + kPieceRecs - 1) / kPieceRecs;
+    const int cb0 = A.cb_lo + cby * A.cbs;
+    const int cbs = min(A.cbs, A.n_colblocks - cb0);   // column blocks of this item
+    if (n_pieces == 1) {
+      // ---- the common case: the chunk is one staged piece; warps take the active column blocks in turn ----
+      const int n = static_cast<int>(n_recs);
+      if (threadIdx.x == 0) issue_piece(ring, chunk, n_recs, 0);
+      if (tail < 0) pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
+      mbar_wait(&ring.full[0], 0u);
+      const Rec* r = &ring.buf[0][0];
+      // head mask of every block of 32 records
+      for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
+        const int32_t kind = i < n ? r[i].kind : REC_OP;
+        const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
+        if (lane == 0) headm[i >> 5] = h;
+      }
+      // activity bytes: thread t -> record t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
+      uint32_t seen = 0u;   // column blocks for which this thread saw an active contribution
+      for (int t = threadIdx.x; t < n * cbs; t += blockDim.x) {
+        const int i = t / cbs, w = t - i * cbs;
+        const int32_t row = r[i].slot;
+        const int32_t kind = r[i].kind;
+        uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
+        uint8_t f = 0;
+        if (kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
         else f = *b;
+        pf[w * kPfPitch + i] = f;
+        if (kind == REC_OP && f) seen |= 1u << w;
       }
-      pf[ww * kPfPitch + i] = f;
-    }
-    __syncthreads();
-    if (live) {
-      bool mine = false;
-      for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[warp * kPfPitch + i] != 0);
-      if (!__any_sync(0xffffffffu, mine)) {
-        // nothing to add: retire the open target; remember the last head for a group that goes on
-        fused_retire<V>(S, L);
-        int last = -1;
-        for (int i = lane; i < n; i += 32)
-          if (r[i].kind != REC_OP) last = i;
-        last = __reduce_max_sync(0xffffffffu, last);
-        if (last >= 0) {
-          S.cur = r[last].slot;
-          S.cur_zero = (r[last].kind == REC_ZMARK);
-          S.acc_valid = false;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
+      if (lane == 0 && seen) atomicOr(&smask, seen);
+      __syncthreads();
+      const uint32_t mask = smask;
+      int k = 0;
+      for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
+        if (k % nwarps != warp) continue;
+        const int w = __ffs(mm) - 1;
+        const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
+        fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, &wlist[warp][0], L);
+      }
+    } else {
+      // ---- a chunk longer than one piece (a target group of more than kPieceRecs contributions): the chunk is
+      // streamed once per set of nwarps column blocks, warp w bound to one column block, state carried across pieces
+      const int n_sets = (cbs + nwarps - 1) / nwarps;
+      const int64_t total = n_pieces * n_sets;
+      if (threadIdx.x == 0)
+        for (int64_t it = 0; it < total && it < kStages; ++it) issue_piece(ring, chunk, n_recs, it % n_pieces, it);
+      if (tail < 0) pdl_wait();
+      FusedState<V> S;
+      S.reset();
+      for (int64_t it = 0; it < total; ++it) {
+        const int64_t p = it % n_pieces;
+        const int set = static_cast<int>(it / n_pieces);
+        const int w = set * nwarps + warp;
+        const bool live = w < cbs;
+        const FusedLane L = fused_lane<V>(A, cb0 + (live ? w : 0), lane);
+        if (p == 0) S.reset();
+        const int st = static_cast<int>(it % kStages);
+        mbar_wait(&ring.full[st], static_cast<uint32_t>((it / kStages) & 1));
+        const int64_t left = n_recs - p * kPieceRecs;
+        const int n = static_cast<int>(left < kPieceRecs ? left : kPieceRecs);
+        const Rec* r = &ring.buf[st][0];
+        for (int t = threadIdx.x; t < n * nwarps; t += blockDim.x) {
+          const int i = t / nwarps, ww = t - i * nwarps;
+          uint8_t f = 0;
+          if (set * nwarps + ww < cbs) {
+            uint8_t* b = A.rowact + static_cast<int64_t>(r[i].slot) * ncb + cb0 + set * nwarps + ww;
+            if (r[i].kind == REC_ZMARK) *b = 0;
+            else f = *b;
+          }
+          pf[ww * kPfPitch + i] = f;
         }
-      } else {
-        fused_piece<V>(r, n, &pf[warp * kPfPitch], S, L);
+        __syncthreads();
+        if (live) {
+          bool mine = false;
+          for (int i = lane; i < n; i += 32) mine |= (r[i].kind == REC_OP && pf[warp * kPfPitch + i] != 0);
+          if (!__any_sync(0xffffffffu, mine)) {
+            // nothing to add: retire the open target; remember the last head for a group that goes on
+            fused_retire<V>(S, L);
+            int last = -1;
+            for (int i = lane; i < n; i += 32)
+              if (r[i].kind != REC_OP) last = i;
+            last = __reduce_max_sync(0xffffffffu, last);
+            if (last >= 0) {
+              S.cur = r[last].slot;
+              S.cur_zero = (r[last].kind == REC_ZMARK);
+              S.acc_valid = false;
+            }
+          } else {
+            fused_piece<V>(r, n, &pf[warp * kPfPitch], S, L);
+          }
+          if (p == n_pieces - 1) fused_retire<V>(S, L);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it + kStages < total) issue_piece(ring, chunk, n_recs, (it + kStages) % n_pieces, it + kStages);
       }
-      if (p == n_pieces - 1) fused_retire<V>(S, L);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && it + kStages < total) issue_piece(ring, chunk, n_recs, (it + kStages) % n_pieces, it + kStages);
+    // ---- the next item, if any ----
+    if (A.n_tail == 0) break;
+    __syncthreads();   // every warp of this CTA has issued its stores
+    if (tail < 0) {
+      if (threadIdx.x == 0) {
+        __threadfence();   // release: this CTA's rows and activity bytes
+        s_last = (atomicAdd(A.done, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+      }
+      __syncthreads();
+      if (!s_last) break;
+      __threadfence();     // acquire: what every other CTA of the launch wrote (drops this SM's L1 lines as well)
+      tail = 0;
+      c = A.tail_c0[0];
+      cby = 0;
+    } else {
+      if (++cby == static_cast<int>(gridDim.y)) {
+        cby = 0;
+        ++c;
+      }
+      if (c == A.tail_c1[tail]) {
+        if (++tail == A.n_tail) break;
+        __threadfence();   // the next tail step reads what this one wrote
+        c = A.tail_c0[tail];
+      }
+    }
   }
 }
 

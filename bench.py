@@ -284,6 +284,10 @@ def main():
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--fused", type=int, default=1, help="reverse level sweep as one kernel per step (0: snapshot + gather)")
     ap.add_argument("--cbs", type=int, default=0, help="fused kernel: column blocks per CTA (0 = automatic)")
+    ap.add_argument("--tail", type=int, default=1, help="fused kernel: tiny steps ride along with the previous launch")
+    ap.add_argument("--dirs", type=int, default=0,
+                    help="EXPERIMENT ONLY: sweep just the first N directions (what one rank of a multi-GPU run holds); "
+                         "the line is then not the named workload and says so in config")
     args = ap.parse_args()
     if args.workload in ("rosenbrock1e7", "ensemble1e5"):
         return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
@@ -341,6 +345,7 @@ def main():
     eng.set_option("chunk_recs", args.chunk)
     eng.set_option("fused", args.fused)
     eng.set_option("cbs", args.cbs)
+    eng.set_option("tail", args.tail)
     if args.streams:
         eng.set_option("streams", args.streams)
 
@@ -360,6 +365,11 @@ def main():
     m = meta[0]
     S, O, G = m["S"], m["O"], m["G"]
     indep, dep = m["indep"], m["dep"]
+    if args.dirs > 0:   # experiment: a rank's share of the directions
+        if mode == 0:
+            indep = np.ascontiguousarray(indep[:args.dirs])
+        else:
+            dep = np.ascontiguousarray(dep[:args.dirs])
     N, M = indep.size, dep.size
     D = N if mode == 0 else M
     work = float(O) * D
@@ -519,7 +529,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * wall_s / K, "ms_per_step_cuda_events": 1e3 * ev_s / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "statements": S, "operations": O, "slots": G, "directions": D,
+        "config": {"workload": wl["desc"] + (f" -- EXPERIMENT: first {args.dirs} directions only" if args.dirs > 0 else ""),
+                   "statements": S, "operations": O, "slots": G, "directions": D,
                    "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}",
                    "schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
                    "steps_in_schedule": eng.stat("n_levels", 0), "pass_dirs": eng.stat("pass_dirs", 0),

@@ -117,6 +117,28 @@ def test_target_groups_longer_than_a_staged_piece(engine, po, cbs):
         engine.set_option("cbs", 0)
 
 
+@pytest.mark.parametrize("name", ["toon_nx128_nt20", "adversarial_1", "rosenbrock_n400", "lw_nx100_nt30"])
+@pytest.mark.parametrize("tail,streams", [(0, 1), (1, 1), (1, 4)])
+def test_tiny_steps_ride_along_with_the_previous_launch(engine, name, tail, streams):
+    """Fused reverse sweep: steps of a chunk or two are run by the last CTA of the previous step's launch
+    (ticket counter + fence) instead of a launch of their own; with and without, on one and on four streams,
+    the Jacobian is the reference's bit for bit."""
+    g = load_golden(name)
+    try:
+        engine.set_option("tail", tail)
+        engine.set_option("streams", streams)
+        for window in (0, 50):
+            upload(engine, g, LEVELS, window)
+            for pass_dirs in (0, 64):
+                engine.set_option("pass_dirs", pass_dirs)
+                assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"])
+            assert engine.stat("used_fused") == 1
+    finally:
+        engine.set_option("tail", 1)
+        engine.set_option("streams", 4)
+        engine.set_option("pass_dirs", 0)
+
+
 # ---- the device-side dependency analysis ------------------------------------------------------------
 @pytest.mark.parametrize("window", [0, 64, 777, 4096])
 def test_levels_match_the_sequential_rule(engine, po, pkg, window):
