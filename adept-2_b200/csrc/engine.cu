@@ -83,7 +83,7 @@ struct Shard {
   bool have_target = false;
   // fused reverse stream (versioned rows, one kernel per step; built on first need)
   bool have_fused = false;
-  Buf ftgt, fchunk, fpar, out_rows, done;
+  Buf ftgt, fchunk, fpar, out_rows, done, trace;
   int64_t n_fchunks = 0, R_f = 0, chunk_recs = 0;
   std::vector<int64_t> step_fchunk;   // [n_levels+2] first fused chunk of each step
   Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
@@ -1058,6 +1058,17 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       s.aux.push_back(st);
       s.aux_ev.push_back(ev);
     }
+#ifdef ADEPT_FUSED_TRACE
+    constexpr size_t kTraceLaunches = 4096;
+    const char* trace_file = getenv("ADEPT_CUDA_TRACE_FILE");
+    const bool trace_on = fused && trace_file && *trace_file;
+    if (trace_on) {
+      std::vector<unsigned long long> init(kTraceLaunches * 8, 0ull);
+      for (size_t k = 0; k < kTraceLaunches; ++k) init[k * 8 + 0] = init[k * 8 + 1] = ~0ull;
+      RET(ensure(errp, s.trace, init.size() * 8));
+      CK(cudaMemcpy(s.trace.p, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    }
+#endif
     if (fused && c->opt_tail) {  // ticket counters of the launches that carry tail steps
       const size_t nb = size_t(nstr) * size_t(s.n_levels + 1) * sizeof(unsigned int);
       RET(ensure(errp, s.done, nb));
@@ -1103,6 +1114,9 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
             --l;
           }
           Bi.done = Bi.n_tail ? s.done.as<unsigned int>() + size_t(i) * size_t(s.n_levels + 1) + size_t(l) : nullptr;
+#ifdef ADEPT_FUSED_TRACE
+          Bi.trace = (i == 0 && trace_on && nl[0] < kTraceLaunches) ? s.trace.as<unsigned long long>() + size_t(nl[0]) * 8 : nullptr;
+#endif
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           const dim3 fgrid(unsigned(c1 - c0), unsigned(g_hi - g_lo)), fblock(twarps * 32);
           if (B.ref_block == 1) launch_pdl(reverse_fused_kernel<V, 0>, fgrid, fblock, st, pdl, Bi);
@@ -1127,6 +1141,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       }
       if (cudaGetLastError() != cudaSuccess) rcs[i] = ADEPT_CUDA_ERR_CUDA;
     };
+    const auto t_issue = std::chrono::steady_clock::now();
     if (nstr == 1) {
       run_stream(0);
     } else {
@@ -1135,6 +1150,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       run_stream(0);
       for (std::thread& t : th) t.join();
     }
+    s.stat["host_issue_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue).count();
     for (int i = 0; i < nstr; ++i) {
       s.launches += nl[i];
       if (rcs[i]) return fail(errp, rcs[i], "launch failed in the reverse level sweep: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1145,6 +1161,20 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         CK(cudaStreamWaitEvent(s.stream, s.aux_ev[i - 1], 0));
       }
     }
+#ifdef ADEPT_FUSED_TRACE
+    if (trace_on) {   // profiling aid: dump the time stamps of stream 0's launches
+      CK(cudaStreamSynchronize(s.stream));
+      std::vector<unsigned long long> h(kTraceLaunches * 8);
+      CK(cudaMemcpy(h.data(), s.trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(trace_file, "w")) {
+        for (size_t k = 0; k < kTraceLaunches && k < size_t(nl[0]); ++k) {
+          for (int q = 0; q < 8; ++q) fprintf(f, "%llu ", h[k * 8 + q]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
+#endif
   }
   CK(cudaGetLastError());
   return 0;

@@ -366,8 +366,21 @@ struct TargetArgs {
   int n_tail;
   int64_t tail_c0[4], tail_c1[4];   // chunk range of every tail step, in sweep order
   unsigned int* done;
+  unsigned long long* trace;   // profiling aid (built with -DADEPT_FUSED_TRACE only): 8 time stamps per launch
 };
 constexpr int kMaxTail = 4;
+#ifdef ADEPT_FUSED_TRACE
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define FUSED_TRACE_MIN(k) do { if (A.trace && threadIdx.x == 0) atomicMin(&A.trace[k], gtimer()); } while (0)
+#define FUSED_TRACE_MAX(k) do { if (A.trace && threadIdx.x == 0) atomicMax(&A.trace[k], gtimer()); } while (0)
+#else
+#define FUSED_TRACE_MIN(k) do { } while (0)
+#define FUSED_TRACE_MAX(k) do { } while (0)
+#endif
 
 // The CTA first fetches, in one round trip and for all its warps, the activity byte of every
 // record of the staged piece (pf); a warp whose column block has no active contribution in the
@@ -767,6 +780,7 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
   int64_t c = A.first_chunk + blockIdx.x;
   int cby = blockIdx.y;
   int tail = -1;   // -1: own item; >= 0: tail step being run
+  FUSED_TRACE_MIN(0);
   for (;;) {
     if (threadIdx.x == 0) {
       if (tail >= 0)
@@ -788,6 +802,7 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       const int n = static_cast<int>(n_recs);
       if (threadIdx.x == 0) issue_piece(ring, chunk, n_recs, 0);
       if (tail < 0) pdl_wait();   // records (immutable) are already in flight; rows and activity bytes come from the previous step
+      if (tail < 0) { FUSED_TRACE_MIN(1); FUSED_TRACE_MAX(2); }
       mbar_wait(&ring.full[0], 0u);
       const Rec* r = &ring.buf[0][0];
       // head mask of every block of 32 records
@@ -813,6 +828,7 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
       if (lane == 0 && seen) atomicOr(&smask, seen);
       __syncthreads();
+      if (tail < 0) FUSED_TRACE_MAX(3);
       const uint32_t mask = smask;
       int k = 0;
       for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
@@ -879,8 +895,10 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       }
     }
     // ---- the next item, if any ----
+    if (tail < 0) FUSED_TRACE_MAX(4);
     if (A.n_tail == 0) break;
     __syncthreads();   // every warp of this CTA has issued its stores
+    if (tail < 0) FUSED_TRACE_MAX(5);
     if (tail < 0) {
       if (threadIdx.x == 0) {
         __threadfence();   // release: this CTA's rows and activity bytes
@@ -904,6 +922,7 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       }
     }
   }
+  FUSED_TRACE_MAX(6);
 }
 
 // ---------------------------------------------------------------------------------------

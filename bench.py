@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--fused", type=int, default=1, help="reverse level sweep as one kernel per step (0: snapshot + gather)")
     ap.add_argument("--cbs", type=int, default=0, help="fused kernel: column blocks per CTA (0 = automatic)")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch between the per-step kernels")
     ap.add_argument("--tail", type=int, default=1, help="fused kernel: tiny steps ride along with the previous launch")
     ap.add_argument("--dirs", type=int, default=0,
                     help="EXPERIMENT ONLY: sweep just the first N directions (what one rank of a multi-GPU run holds); "
@@ -346,6 +347,7 @@ def main():
     eng.set_option("fused", args.fused)
     eng.set_option("cbs", args.cbs)
     eng.set_option("tail", args.tail)
+    eng.set_option("pdl", args.pdl)
     if args.streams:
         eng.set_option("streams", args.streams)
 
@@ -417,6 +419,7 @@ def main():
     wall_s, ev_s = float(wall[0]), float(wall[1])
     value = work * K / wall_s
 
+    host_issue_ms = eng.stat("host_issue_ms", None)   # host time spent enqueueing the last timed sweep's launches
     # dominant kernel, every launch bracketed by CUDA events on its own stream (one extra step)
     eng.set_option("time_kernels", 1)
     step()
@@ -534,7 +537,7 @@ def main():
                    "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}",
                    "schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
                    "steps_in_schedule": eng.stat("n_levels", 0), "pass_dirs": eng.stat("pass_dirs", 0),
-                   "n_passes": eng.stat("n_passes", 0),
+                   "n_passes": eng.stat("n_passes", 0), "host_issue_ms": host_issue_ms,
                    "l2": "inputs larger than L2: tape streams %.0f MB + workspace %.0f MB per step" %
                          (16e-6 * (O + S), 8e-6 * G * min(D, eng.stat("pass_dirs", D) or D))},
         "clocks": clocks,
