@@ -493,6 +493,10 @@ def main():
     # per-statement part too, so it is credited with the whole formula
     dom_bytes = 16.0 * work / world if used == 2 and mode == 1 and not used_fused else bpo * work / world
     roof = None
+    n_passes = max(1.0, eng.stat("n_passes", 1.0) or 1.0)
+    pass_dirs = eng.stat("pass_dirs", 0.0) or float(D)
+    d_rank = float(D) / world
+    last_pass_share = max(0.0, d_rank - (n_passes - 1.0) * pass_dirs) / d_rank if n_passes > 1 else 1.0
     if dom_ms and dom_launches:
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         kname = {(1, 2.0): "reverse_target_kernel<2>", (0, 2.0): "forward_level_kernel<2,sparse>", (1, 1.0): "replay_reverse_kernel",
@@ -505,7 +509,8 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes / dom_launches,
                 "avg_launch_us": 1e3 * dom_ms / dom_launches,
                 "ms_by_quarter_of_sweep": dom_quarters,
-                "whole_sweep_frac": (bpo * work / world) / (sweep_ms / 1e3) / 1e9 / peak if sweep_ms else None,
+                # sweep_ms covers the LAST pass only: credit it with that pass's share of the directions
+                "whole_sweep_frac": (bpo * work / world * last_pass_share) / (sweep_ms / 1e3) / 1e9 / peak if sweep_ms else None,
                 "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
                         "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}
 

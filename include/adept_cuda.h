@@ -147,8 +147,13 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
                      plus the reverse snapshot <= 200 KB) run in the shared-memory-resident kernel; 0 = never
      "chunk_recs"    records per level chunk = one CTA's share of a step (0 = default 64, max 256); takes effect at
                      the next adept_cuda_upload_tape
+     "fused"         1 (default) = the level-scheduled reverse sweep runs ONE kernel per step over versioned rows
+                     (two workspace rows per slot, no snapshot buffer); 0 = snapshot + gather, two kernels per step
+     "cbs"           fused kernel: 64-direction column blocks per CTA (1..32; 0 = automatic)
+     "tail"          fused kernel: 1 (default) = steps of a chunk or two are run by the last CTA of the previous step's
+                     launch instead of a launch of their own
      "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
-                     between steps; 0 (default) = two launches per step (measured faster on B200)
+                     between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
 */
@@ -158,7 +163,9 @@ int  adept_cuda_set_option(adept_cuda_ctx* ctx, const char* key, int64_t value);
    "kernel_launches" (cumulative count of this library's own kernel launches),
    "replay_ms" (CUDA-event time of the last replay: zero-fill+seed+sweep+extract(+gather)),
    "sweep_ms" (the replay kernels alone), "upload_ms", "analysis_ms", "d2h_ms",
-   "used_schedule" (1 tape-ordered / 2 level / 3 level with shared-memory gradients), "pass_dirs", "n_passes". */
+   "used_schedule" (1 tape-ordered / 2 level / 3 level with shared-memory gradients), "used_fused", "pass_dirs",
+   "n_passes", "an_window_ms" / "an_forward_ms" / "an_target_ms" / "an_fused_ms" (phases of the schedule build; the two
+   reverse streams are built on first use), "host_issue_ms" (host time spent enqueueing the last reverse level sweep). */
 int  adept_cuda_get_stat(const adept_cuda_ctx* ctx, const char* key, double* value);
 
 /* Copies the per-statement level (1-based; level[0]=0 for the sentinel) of the last
