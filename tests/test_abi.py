@@ -52,3 +52,37 @@ def test_product_never_imports_the_oracle():
                 if "pyoracle" in text or "liboracle" in text or "libadept_ref" in text:
                     bad.append(f)
     assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_every_documented_option_is_implemented_and_vice_versa():
+    """include/adept_cuda.h documents the option keys of adept_cuda_set_option; the engine must accept exactly
+    those (an option that exists in only one of the two places is a documentation or a dead-code bug)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "adept_cuda.h")).read()
+    block = header[header.index("/* Options (key, value):"):header.index("int  adept_cuda_set_option")]
+    documented = set(re.findall(r'^\s{5}"([a-z_]+)"', block, flags=re.M))
+    engine = open(os.path.join(root, "adept-2_b200", "csrc", "engine.cu")).read()
+    body = engine[engine.index("int adept_cuda_set_option"):engine.index("int adept_cuda_get_stat")]
+    implemented = set(re.findall(r'k == "([a-z_]+)"', body))
+    assert documented == implemented, (sorted(documented - implemented), sorted(implemented - documented))
+
+
+def test_fused_kernel_is_built_in_all_three_skip_rule_variants(pkg):
+    """reverse_fused_kernel<V=2, LP>: LP = 0 (P = 1), 1 (P = 2), 2 (P >= 4) -- the reference's block widths
+    (adept/jacobian.cpp:392-407) -- plus the two-kernel form it can fall back to."""
+    out = subprocess.run(["cuobjdump", "-sass", pkg._abi.LIB_PATH], capture_output=True, text=True).stdout
+    for lp in (0, 1, 2):
+        assert f"reverse_fused_kernelILi2ELi{lp}EE" in out
+    assert "reverse_target_kernelILi2EE" in out and "reverse_snapshot_kernel" in out
+
+
+def test_traffic_file_names_the_kernels_the_bench_reports():
+    """profiles/traffic.json feeds roofline.traffic; bench.py only copies an entry whose kernel name matches
+    the kernel it reports for that workload."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tr = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    bench = open(os.path.join(root, "bench.py")).read()
+    for wl in ("toon4096", "synthetic1e7_rev"):
+        assert tr[wl]["kernel"] in bench and tr[wl]["dram_bytes_per_launch"] > 0
