@@ -80,8 +80,6 @@ def test_thread_count_does_not_change_the_result(tmp_path):
 
 @needs_build
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: the first GPU execution of this "
-                                         "test is the driver's round-end run (the CPU half above is verified)")
 @pytest.mark.parametrize("n_members", [1, 257])
 def test_zz_helper_feeds_the_batch_entry_point(po, tmp_path, n_members):
     d = run_check(tmp_path, n_members, "gpu")
