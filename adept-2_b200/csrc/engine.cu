@@ -1310,7 +1310,8 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       if (last) CK(cudaEventRecord(s.ev[3], s.stream));
       const dim3 eg(unsigned((n + 31) / 32), unsigned((n_out + 31) / 32));
       extract_kernel<<<eg, dim3(32, 8), 0, s.stream>>>(g, K, out_rows_dev, n_out, int(n), d0 - d_base, out,
-                                                        stride_i, stride_d);
+                                                        stride_i, stride_d, fused ? s.rowact.as<uint8_t>() : nullptr,
+                                                        ncb_pass, 32 * V);
       s.launches += 1;
       ++n_passes;
     }

@@ -1060,16 +1060,26 @@ __global__ void seed_kernel(double* g, int64_t K, const int32_t* seed_slot, int6
 // out[i*stride_i + (d0+j)*stride_j] = g[out_slot[i]*K + j], i < n_out, j < n_dirs.
 // 32x32 tiles through shared memory so that both the row reads and the writes coalesce
 // whichever of stride_i / stride_j is the unit one.
+// rowact != nullptr (fused reverse sweep): a block whose activity byte is 0 is all +0.0 WHATEVER memory
+// holds -- a ZMARK only clears the byte of the row it opens, and when no active contribution lands on that
+// row nothing is stored, so the memory still shows the version before last.  The sweep's own reads are all
+// guarded by the byte; so is this one.
 __global__ void extract_kernel(const double* __restrict__ g, int64_t K, const int32_t* __restrict__ out_slot,
                                int64_t n_out, int n_dirs, int64_t d0, double* __restrict__ out,
-                               int64_t stride_i, int64_t stride_j) {
+                               int64_t stride_i, int64_t stride_j, const uint8_t* __restrict__ rowact, int ncb,
+                               int block_dirs) {
   __shared__ double tile[32][33];
   const int64_t i0 = static_cast<int64_t>(blockIdx.y) * 32;
   const int j0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t i = i0 + r;
     const int j = j0 + threadIdx.x;
-    if (i < n_out && j < n_dirs) tile[r][threadIdx.x] = g[static_cast<int64_t>(out_slot[i]) * K + j];
+    if (i < n_out && j < n_dirs) {
+      const int64_t row = out_slot[i];
+      double v = 0.0;
+      if (!rowact || rowact[row * ncb + j / block_dirs]) v = g[row * K + j];
+      tile[r][threadIdx.x] = v;
+    }
   }
   __syncthreads();
   if (stride_i < stride_j) {  // consecutive i are close in memory: lanes run over i

@@ -224,13 +224,17 @@ def radiance_tape(surface_temperature=294.0, temperature=None):
 
 
 def random_small_tape(rng, n_statements, n_slots, max_ops=5, n_indep=3, n_dep=3, zero_op_prob=0.1,
-                      self_ref_prob=0.2, dup_prob=0.2):
+                      self_ref_prob=0.2, dup_prob=0.2, lhs_any_prob=0.0):
     """Adversarial little tapes for parity tests: heavy slot reuse, statements that read their own
-    LHS, repeated operands, zero-operand statements (``x = constant``)."""
+    LHS, repeated operands, zero-operand statements (``x = constant``).  With lhs_any_prob > 0 that share
+    of the statements may write ANY slot, the independents included (an independent that is overwritten
+    during the recording: its Jacobian column sees only what happened before the first overwrite)."""
     stmt = [(-1, 0)]
     mult, idx = [], []
     for _ in range(n_statements):
         lhs = int(rng.integers(n_indep, n_slots))
+        if lhs_any_prob > 0.0 and rng.random() < lhs_any_prob:
+            lhs = int(rng.integers(0, n_slots))
         if rng.random() >= zero_op_prob:
             k = int(rng.integers(1, max_ops + 1))
             for _ in range(k):

@@ -87,25 +87,46 @@ def fused_stream(stmt, mult, idx, G, level):
 
 
 def replay_fused(kind, row, m, rstep, fpar, G, g0):
-    """One adjoint sweep of gradient vector(s) g0[G, ...] through the fused stream."""
+    """One adjoint sweep of gradient vector(s) g0[G, ...] through the fused stream, with the device's
+    activity-flag semantics (replay_kernels.cuh, reverse_fused_kernel): act[row] == False means "the row is
+    all +0.0 whatever memory holds".  A ZMARK only clears the flag of the row it opens; a group is stored
+    (and its flag set) only when an ACTIVE contribution reached it; every read -- the sweep's and the final
+    extraction's -- goes through the flag.  Memory rows that are never stored keep stale data on purpose."""
     g = np.zeros((2 * G,) + g0.shape[1:])
     g[:G] = g0
+    act = np.zeros(2 * G, bool)
+    act[:G] = np.any(g0.reshape(G, -1) != 0.0, axis=1)      # the seeds
+    stale = np.full_like(g[0], 777.0)                        # what an unguarded read of a dead row would see
     for st in np.unique(rstep)[::-1]:
         sel = np.nonzero(rstep == st)[0]
-        old = g.copy()                       # every read of a step sees the rows as they were when it began
+        old, old_act = g.copy(), act.copy()   # every read of a step sees rows and flags as they were when it began
         cur = acc = None
+        dirty = False
+
+        def retire():
+            if cur is not None and dirty:
+                g[cur] = acc
+                act[cur] = True
+
         for i in sel:
             if kind[i] != OP:
-                if cur is not None:
-                    g[cur] = acc
+                retire()
                 cur = row[i]
-                acc = old[cur].copy() if kind[i] == MARK else np.zeros_like(old[cur])
-            else:
-                a = old[row[i]]
-                acc = acc + m[i] * a         # multiply, round, add, round (numpy does not contract)
-        if cur is not None:
-            g[cur] = acc
-    return g[np.arange(G) + fpar * G]
+                dirty = False
+                if kind[i] == ZMARK:
+                    act[cur] = False          # new version of an LHS slot: +0.0 until a contribution lands
+                    acc = np.zeros_like(old[cur])
+                else:
+                    acc = old[cur].copy() if old_act[cur] else np.zeros_like(old[cur])
+            elif old_act[row[i]]:
+                acc = acc + m[i] * old[row[i]]   # multiply, round, add, round (numpy does not contract)
+                dirty = True
+        retire()
+    rows = np.arange(G) + fpar * G
+    out = g[rows]
+    out[~act[rows]] = 0.0                     # extract_kernel consults the flag
+    g[~act] = stale                           # (the stale memory must not be what the caller sees)
+    return out
 
 
 def reference_adjoint(po, t, g0):
@@ -137,3 +158,40 @@ def test_fused_stream_random_tapes(po, pkg, seed):
     got = replay_fused(*ks, G, g0)
     for d in range(3):
         assert same_bits(got[:, d], reference_adjoint(po, t, np.ascontiguousarray(g0[:, d])))
+
+
+def overwritten_independent_tape():
+    """X is an independent AND an LHS, overwritten three times with a break in the self-reference
+    chain:  s1 X = 2*X;  s2 X = const;  s3 X = 3*X;  s4 Y = X.  dY/dX(initial) = 0, but a fused sweep that
+    extracts row memory instead of (flag ? memory : 0) returns the stale 3 of two versions earlier."""
+    X, Y = 0, 1
+    stmt = np.array([[-1, 0], [X, 1], [X, 1], [X, 2], [Y, 3]], np.int32)
+    return dict(stmt=stmt, mult=np.array([2.0, 3.0, 1.0]), idx=np.array([X, X, X], np.int32), max_gradient=3,
+                indep=np.array([X], np.int32), dep=np.array([Y], np.int32))
+
+
+def test_fused_stream_keeps_dead_rows_dead(po):
+    t = overwritten_independent_tape()
+    G = t["max_gradient"]
+    _, level = po.levels(t["stmt"], t["idx"], G, 2, window=65536, huge=65536, pack=1)
+    ks = fused_stream(t["stmt"], t["mult"], t["idx"], G, level)
+    g0 = np.zeros(G)
+    g0[1] = 1.0
+    got = replay_fused(*ks, G, g0)
+    want = reference_adjoint(po, t, g0)
+    assert want[0] == 0.0 and same_bits(got, want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fused_stream_random_tapes_with_overwritten_independents(po, pkg, seed):
+    """Unit seeds (as a Jacobian sweep has them) on tapes whose LHS may be ANY slot, independents included."""
+    rng = np.random.default_rng(900 + seed)
+    t = pkg.tapegen.random_small_tape(rng, int(rng.integers(30, 600)), int(rng.integers(8, 40)), n_indep=4, n_dep=3,
+                                      zero_op_prob=0.3, lhs_any_prob=0.5)
+    G = t["max_gradient"]
+    _, level = po.levels(t["stmt"], t["idx"], G, 2, window=53, huge=65536, pack=1)
+    ks = fused_stream(t["stmt"], t["mult"], t["idx"], G, level)
+    for d in t["dep"]:
+        g0 = np.zeros(G)
+        g0[d] = 1.0
+        assert same_bits(replay_fused(*ks, G, g0), reference_adjoint(po, t, g0))

@@ -171,6 +171,36 @@ def test_random_tapes(engine, po, pkg, seed):
         assert same_bits(engine.tangent_linear(g0, True, flags), po.tangent_linear(t["stmt"], t["mult"], t["idx"], g0))
 
 
+def test_overwritten_independents_leave_no_stale_rows(engine, po, pkg):
+    """ADVICE r1 (high): in the fused reverse sweep a ZMARK only clears the activity byte of the row it opens;
+    when no active contribution lands on that row nothing is stored and the memory still shows the version
+    before last.  X is an independent AND an LHS (s1 X=2X; s2 X=const; s3 X=3X; s4 Y=X): the reference returns
+    dY/dX = 0, an extraction that ignores the byte returns the stale 3."""
+    from test_fused_stream_model import overwritten_independent_tape
+    t = overwritten_independent_tape()
+    for schedule in (LEVELS, UNFUSED, ORDERED, SMALLG):
+        upload(engine, t, schedule)
+        check_jacobians(engine, po, t, f"overwritten independent, schedule {schedule}")
+    upload(engine, t, LEVELS)
+    assert engine.stat("used_fused") == 1 and engine.jacobian(1, t["indep"], t["dep"])[0] == 0.0
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_tapes_whose_independents_are_overwritten(engine, po, pkg, seed):
+    """LHS drawn from ALL slots (independents included), many x = constant statements: chains of versions
+    with breaks, in every schedule, single and multiple passes."""
+    rng = np.random.default_rng(700 + seed)
+    t = pkg.tapegen.random_small_tape(rng, int(rng.integers(30, 3000)), int(rng.integers(12, 200)),
+                                      n_indep=int(rng.integers(1, 12)), n_dep=int(rng.integers(1, 7)),
+                                      zero_op_prob=0.3, lhs_any_prob=0.5)
+    for schedule, window in ((LEVELS, 0), (LEVELS, 53), (UNFUSED, 53), (SMALLG, 53), (ORDERED, 0)):
+        upload(engine, t, schedule, window)
+        check_jacobians(engine, po, t, f"seed {seed} schedule {schedule} window {window}")
+        engine.set_option("pass_dirs", 32)
+        check_jacobians(engine, po, t, f"seed {seed} schedule {schedule} window {window} passes")
+        engine.set_option("pass_dirs", 0)
+
+
 def test_empty_and_tiny_tapes(engine, po):
     # only the sentinel: every Jacobian entry is d(slot)/d(slot)
     t = dict(stmt=np.array([[-1, 0]], np.int32), mult=np.zeros(0), idx=np.zeros(0, np.int32), max_gradient=4,
