@@ -5,6 +5,7 @@
 //   Stack::jacobian_forward / jacobian_reverse   (reference adept/jacobian.cpp:127-647)
 //   Stack::compute_tangent_linear / compute_adjoint (reference adept/Stack.cpp:139-190)
 // Host code here is plumbing (memory, streams, NCCL); there is no CPU replay path.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <nccl.h>
 
@@ -60,7 +61,7 @@ struct LongStmt {
 struct Shard {
   int dev = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   ncclComm_t comm = nullptr;
   int sm_count = 148;
   // pinned staging ring for pageable uploads
@@ -69,7 +70,8 @@ struct Shard {
   // the tape as recorded
   Buf stmt, mult, idx;
   int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
-  bool have_tape = false;
+  bool have_tape = false;       // the recorded arrays are on this device
+  bool have_schedule = false;   // build_schedule has run for them (validation, level analysis, forward stream)
   bool have_tape_streams = false;
   bool has_nonfinite = false;  // some multiplier is inf/NaN: forward block-sparsity is then off
   // tape-order streams
@@ -94,12 +96,20 @@ struct Shard {
   std::vector<int64_t> level_first;   // [n_levels+2] first schedule position of each step
   std::vector<int64_t> step_group;    // [n_levels+2] first target group of each step
   std::vector<int64_t> step_tchunk;   // [n_levels+2] first target chunk of each step
-  std::vector<LongStmt> long_stmts;
+  std::vector<int64_t> step_recs;       // [n_levels+2] forward records (operations + statements) of each step
+  std::vector<std::string> prof_log;    // option "profile_every": one line per launch handed to the profiler
+  std::vector<LongStmt> long_stmts;     // sorted by schedule position (hence by step)
+  Buf long_tab;                         // device copy: {b, e} record range of every long statement, same order
   // workspace
-  Buf g, abuf, rowact, aflag, seed_slots, out_slots, out, g1, a1, scratch;
+  Buf g, abuf, rowact, aflag, seed_slots, out_slots, out, g1, a1, scratch, agree_buf;
   // optional per-launch timing of the dominant replay kernel (option "time_kernels")
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
+  // the replay kernels of EVERY pass of a Jacobian are bracketed by an event pair on the shard's stream: their sum
+  // is "sweep_ms", measured inside whatever region the caller times (PDL and streams as in production)
+  std::vector<cudaEvent_t> pev;
+  size_t pev_used = 0;
+  double sweep_launches = 0;   // launches of the replay kernel(s) between those events, last Jacobian
   std::vector<Buf> pool;  // analysis temporaries (build_schedule)
   std::vector<cudaStream_t> aux;      // extra streams: independent direction ranges of one sweep
   std::vector<cudaEvent_t> aux_ev;
@@ -130,6 +140,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_profile_every = 0;  // > 0: cudaProfilerStart/Stop around every Nth launch of a level sweep (ncu --profile-from-start off)
   // stats
   std::map<std::string, double> stat;
   std::string err;
@@ -167,6 +178,12 @@ int fail(std::string* e, int code, const char* fmt, ...) {
     if (r_ != ncclSuccess)                                                                         \
       return fail(errp, ADEPT_CUDA_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), \
                   __FILE__, __LINE__);                                                             \
+  } while (0)
+// inside ncclGroupStart/ncclGroupEnd: remember the first failure, keep going, so that the group is always closed
+#define NKG(var, call)                                   \
+  do {                                                   \
+    ncclResult_t r_ = (call);                            \
+    if (r_ != ncclSuccess && (var) == ncclSuccess) (var) = r_; \
   } while (0)
 #define RET(call)                \
   do {                           \
@@ -317,6 +334,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   CK(cudaSetDevice(s.dev));
   const int64_t S = s.n_stmt - 1, O = s.n_ops, R = O + S;
   s.R = R;
+  s.have_schedule = false;
   s.have_levels = false;
   s.have_tape_streams = false;
   s.have_target = false;
@@ -332,6 +350,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   if (R >= (int64_t(1) << 31) - 1)
     return fail(errp, ADEPT_CUDA_ERR_LIMIT, "tape too long: n_ops + n_statements = %lld >= 2^31", (long long)R);
   const int T = 256;
+  auto tp = std::chrono::steady_clock::now();
   // 1. validate (a bad slot would otherwise be a wild device access)
   RET(ensure(errp, s.scratch, 64));
   CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
@@ -345,15 +364,21 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   if (flags & 1)
     return fail(errp, ADEPT_CUDA_ERR_RANGE,
                 "malformed tape: a slot index is outside [0,max_gradient) or statement ends are not monotone");
+  s.stat["an_validate_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count();
+  tp = std::chrono::steady_clock::now();
   // 2. tape-order streams
   const int64_t one_chunk_host[2] = {0, R};
   RET(ensure(errp, s.one_chunk, sizeof one_chunk_host));
   CK(cudaMemcpyAsync(s.one_chunk.p, one_chunk_host, sizeof one_chunk_host, cudaMemcpyHostToDevice, s.stream));
   CK(cudaStreamSynchronize(s.stream));  // one_chunk_host is a stack variable
-  if (S == 0) return 0;
+  if (S == 0) { s.have_schedule = true; return 0; }
   s.have_tape_streams = false;
   const bool want_levels = (c->opt_schedule != 1) && (S >= kMinLevelStatements || c->opt_schedule == 2);
-  if (!want_levels) return ensure_tape_streams(s);
+  if (!want_levels) {
+    RET(ensure_tape_streams(s));
+    s.have_schedule = true;
+    return 0;
+  }
 
   // Temporaries live in a per-shard pool that survives the call (re-uploads of similar tapes then cost
   // no cudaMalloc/cudaFree, which dominated and jittered the analysis time); a pool above
@@ -365,7 +390,6 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       &lfirst = s.pool[11], &flag = s.pool[12], &cid = s.pool[13], &lchunk = s.pool[14], &lo = s.pool[22], &lc = s.pool[23];
   Buf& pos_in_sched = s.pos_in_sched;
 
-  auto tp = std::chrono::steady_clock::now();
   auto lap = [&](const char* key) {
     cudaStreamSynchronize(s.stream);
     auto now = std::chrono::steady_clock::now();
@@ -592,42 +616,106 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   step_info_kernel<<<unsigned((n_levels + 2 + T - 1) / T), T, 0, s.stream>>>(s.d_level_first.as<int64_t>(), s.foff.as<int64_t>(),
                                                                            n_levels, s.sg_fwd_info.as<longlong4>());
   s.launches += 1;
-  CK(cudaStreamSynchronize(s.stream));
-  // 6. long statements (rare): listed for the single-direction forward sweep
   {
-    const int max_long = 4096;
-    RET(ensure(errp, lo, size_t(max_long) * 8));
-    RET(ensure(errp, lc, 16));
-    CK(cudaMemsetAsync(lc.p, 0, 16, s.stream));
-    find_long_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), S, kLongThreshold,
-                                                                     lo.as<int64_t>(), lc.as<int>(), max_long);
-    s.launches += 1;
-    int nl = 0;
-    std::vector<int64_t> js(max_long);
-    CK(cudaMemcpyAsync(&nl, lc.p, 4, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaMemcpyAsync(js.data(), lo.p, size_t(max_long) * 8, cudaMemcpyDeviceToHost, s.stream));
+    std::vector<longlong4> info(size_t(n_levels) + 2);
+    CK(cudaMemcpyAsync(info.data(), s.sg_fwd_info.p, info.size() * 32, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
-    if (nl > max_long)
-      return fail(errp, ADEPT_CUDA_ERR_LIMIT, "more than %d statements longer than %lld operands", max_long,
-                  (long long)kLongThreshold);
-    js.resize(nl);
-    std::sort(js.begin(), js.end());
-    int64_t ends[2];
-    for (int64_t j : js) {
+    s.step_recs.assign(size_t(n_levels) + 2, 0);
+    for (int32_t l = 1; l <= n_levels; ++l) s.step_recs[l] = info[l].w - info[l].z;
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  // 6. long statements (rare): listed for the single-direction forward sweep.  The list grows to whatever the tape
+  //    needs (a recorded dense mat-vec has one long statement per row); {j, b, e} triples come back in one copy.
+  {
+    int64_t cap_long = 4096;
+    int nl = 0;
+    std::vector<int64_t> trip;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      RET(ensure(errp, lo, size_t(cap_long) * 24));
+      RET(ensure(errp, lc, 16));
+      CK(cudaMemsetAsync(lc.p, 0, 16, s.stream));
+      find_long_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), S, kLongThreshold,
+                                                                       lo.as<int64_t>(), lc.as<int>(), int(cap_long));
+      s.launches += 1;
+      CK(cudaMemcpyAsync(&nl, lc.p, 4, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+      if (nl <= cap_long) break;
+      cap_long = nl;
+    }
+    trip.resize(size_t(nl) * 3);
+    if (nl > 0) {
+      CK(cudaMemcpyAsync(trip.data(), lo.p, size_t(nl) * 24, cudaMemcpyDeviceToHost, s.stream));
+      CK(cudaStreamSynchronize(s.stream));
+    }
+    std::vector<int> order(nl);
+    for (int k = 0; k < nl; ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return trip[size_t(a) * 3] < trip[size_t(b) * 3]; });
+    std::vector<int64_t> tab(size_t(std::max(nl, 1)) * 2);
+    for (int k = 0; k < nl; ++k) {
       LongStmt L;
-      L.j = j;
+      L.j = trip[size_t(order[k]) * 3];
       // step of schedule position j: last l with level_first[l] <= j
-      L.level = int32_t(std::upper_bound(s.level_first.begin() + 1, s.level_first.begin() + n_levels + 1, j) -
+      L.level = int32_t(std::upper_bound(s.level_first.begin() + 1, s.level_first.begin() + n_levels + 1, L.j) -
                         s.level_first.begin()) - 1;
-      CK(cudaMemcpy(ends, s.foff.as<int64_t>() + j, 16, cudaMemcpyDeviceToHost));
-      L.b = ends[0];
-      L.e = ends[1];
+      L.b = trip[size_t(order[k]) * 3 + 1];
+      L.e = trip[size_t(order[k]) * 3 + 2];
+      tab[size_t(k) * 2] = L.b;
+      tab[size_t(k) * 2 + 1] = L.e;
       s.long_stmts.push_back(L);
     }
+    RET(ensure(errp, s.long_tab, tab.size() * 8));
+    CK(cudaMemcpyAsync(s.long_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaStreamSynchronize(s.stream));   // tab is a host vector
   }
   CK(cudaGetLastError());
   s.have_levels = true;
+  s.have_schedule = true;
   return 0;
+}
+
+// The schedule of the tape on this shard, built on first need.  adept_cuda_upload_tape builds it eagerly in a
+// one-process context; in a one-process-per-GPU job (adept_cuda_join) it is built by adept_cuda_share_tape on ALL
+// ranks at the same time, after the broadcast -- not on the root first and on its peers afterwards.
+int ensure_schedule(adept_cuda_ctx* c, Shard& s) {
+  std::string* errp = &s.err;
+  if (s.have_schedule) return 0;
+  if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
+  auto t0 = std::chrono::steady_clock::now();
+  RET(build_schedule(c, s));
+  CK(cudaStreamSynchronize(s.stream));
+  s.stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+void publish_schedule_stats(adept_cuda_ctx* c) {
+  const Shard& s = c->sh[0];
+  c->stat["n_levels"] = s.n_levels;
+  c->stat["n_chunks"] = double(s.n_chunks);
+  c->stat["n_records"] = double(s.R);
+  c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
+  c->stat["kernel_launches"] = c->total_launches();
+  for (const char* k : {"analysis_ms", "an_validate_ms", "an_window_ms", "an_pack_ms", "an_forward_ms", "an_target_ms", "an_fused_ms"}) {
+    auto it = s.stat.find(k);
+    if (it != s.stat.end()) c->stat[k] = it->second;
+  }
+}
+
+// One-process-per-GPU jobs: every rank contributes its local status; all ranks get the worst one, so that a
+// failure on one rank (a bad argument, an allocation that did not fit) makes EVERY rank leave before the next
+// collective instead of leaving its peers waiting in it.
+int agree(adept_cuda_ctx* c, int local_rc) {
+  if (!c->multi_process || c->world <= 1) return local_rc;
+  Shard& s = c->sh[0];
+  std::string* errp = &c->err;
+  CK(cudaSetDevice(s.dev));
+  RET(ensure(errp, s.agree_buf, 16));
+  int v = local_rc;
+  CK(cudaMemcpyAsync(s.agree_buf.p, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
+  NK(ncclAllReduce(s.agree_buf.p, s.agree_buf.p, 1, ncclInt, ncclMax, s.comm, s.stream));
+  CK(cudaMemcpyAsync(&v, s.agree_buf.p, sizeof v, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  if (v && !local_rc) return fail(errp, v, "another rank failed this collective call (status %d)", v);
+  return local_rc;
 }
 
 
@@ -887,6 +975,18 @@ int mark(Shard& s) {
   return 0;
 }
 
+// next event of the per-pass pool, recorded on the shard's stream
+int mark_pass(Shard& s) {
+  std::string* errp = &s.err;
+  if (s.pev_used == s.pev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    s.pev.push_back(e);
+  }
+  CK(cudaEventRecord(s.pev[s.pev_used++], s.stream));
+  return 0;
+}
+
 // One sweep over the resident pass (g already zeroed and seeded).  mode: 0 forward, 1 reverse.
 int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t K, int64_t n_dirs,
                  const SweepPlan& plan, bool fused) {
@@ -900,6 +1000,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
   A.ref_block = c->opt_ref_block;
   const int threads = plan.warps * 32;
   const unsigned gy = unsigned((A.n_colblocks + plan.warps - 1) / plan.warps);
+  s.stat["sweep_streams"] = 1;
   if (!plan.use_levels) {
     RET(ensure_tape_streams(s));
     A.recs = (mode == 0 ? s.fwd_t : s.rev_t).as<Rec>();
@@ -930,7 +1031,8 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const int groups = (all_cb + fwarps - 1) / fwarps;
     int nstr = std::max(1, std::min<int>(c->opt_streams, groups));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= kWideStepCtas || c->opt_time_kernels) nstr = 1;
+    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= kWideStepCtas || c->opt_time_kernels || c->opt_profile_every) nstr = 1;
+    s.stat["sweep_streams"] = nstr;
     while (int(s.aux.size()) < nstr - 1) {
       cudaStream_t st;
       cudaEvent_t ev;
@@ -960,8 +1062,24 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         Fi.first_chunk = c0;
         const dim3 grid(unsigned(c1 - c0), unsigned(g_hi - g_lo));
         if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-        if (sparse) launch_pdl(forward_level_kernel<V, true>, grid, dim3(fwarps * 32), st, pdl, Fi);
-        else launch_pdl(forward_level_kernel<V, false>, grid, dim3(fwarps * 32), st, pdl, Fi);
+        const bool prof = c->opt_profile_every > 0 && (int64_t(nl[i]) % c->opt_profile_every) == 0;
+        if (prof) {
+            cudaStreamSynchronize(st);
+            cudaProfilerStart();
+        }
+        cudaError_t le;
+        if (sparse) le = launch_pdl(forward_level_kernel<V, true>, grid, dim3(fwarps * 32), st, pdl && !prof, Fi);
+        else le = launch_pdl(forward_level_kernel<V, false>, grid, dim3(fwarps * 32), st, pdl && !prof, Fi);
+        if (le != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+        if (prof) {
+          cudaStreamSynchronize(st);
+          cudaProfilerStop();
+          char line[160];
+          snprintf(line, sizeof line, "fwd step %d stmts %lld recs %lld dirs %lld grid %u %u", int(l),
+                   (long long)(s.level_first[l + 1] - s.level_first[l]), (long long)s.step_recs[l],
+                   (long long)n_dirs, grid.x, grid.y);
+          s.prof_log.push_back(line);
+        }
         if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         nl[i] += 1;
       }
@@ -1048,8 +1166,9 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     int nstr = std::max(1, std::min<int>(c->opt_streams, (all_cb + gwidth - 1) / gwidth));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
     if (double(fused ? s.n_fchunks : s.n_tchunks) / std::max(1, s.n_levels) * ((all_cb + gwidth - 1) / gwidth) >= kWideStepCtas ||
-        c->opt_time_kernels)
+        c->opt_time_kernels || c->opt_profile_every)
       nstr = 1;
+    s.stat["sweep_streams"] = nstr;
     while (int(s.aux.size()) < nstr - 1) {
       cudaStream_t st;
       cudaEvent_t ev;
@@ -1101,6 +1220,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
           const int64_t c0 = s.step_fchunk[l], c1 = s.step_fchunk[l + 1];
           if (c1 <= c0) continue;
           Bi.first_chunk = c0;
+          const int32_t l_top = l;
           // steps of a chunk or two that follow ride along with this launch (run by its last CTA)
           Bi.n_tail = 0;
           while (c->opt_tail && Bi.n_tail < kMaxTail && l - 1 >= 1) {
@@ -1119,9 +1239,27 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
 #endif
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           const dim3 fgrid(unsigned(c1 - c0), unsigned(g_hi - g_lo)), fblock(twarps * 32);
-          if (B.ref_block == 1) launch_pdl(reverse_fused_kernel<V, 0>, fgrid, fblock, st, pdl, Bi);
-          else if (B.ref_block == 2) launch_pdl(reverse_fused_kernel<V, 1>, fgrid, fblock, st, pdl, Bi);
-          else launch_pdl(reverse_fused_kernel<V, 2>, fgrid, fblock, st, pdl, Bi);
+          const bool prof = c->opt_profile_every > 0 && (int64_t(nl[i]) % c->opt_profile_every) == 0;
+          if (prof) {
+            cudaStreamSynchronize(st);
+            cudaProfilerStart();
+          }
+          cudaError_t le;
+          if (B.ref_block == 1) le = launch_pdl(reverse_fused_kernel<V, 0>, fgrid, fblock, st, pdl && !prof, Bi);
+          else if (B.ref_block == 2) le = launch_pdl(reverse_fused_kernel<V, 1>, fgrid, fblock, st, pdl && !prof, Bi);
+          else le = launch_pdl(reverse_fused_kernel<V, 2>, fgrid, fblock, st, pdl && !prof, Bi);
+          if (le != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
+          if (prof) {
+            cudaStreamSynchronize(st);
+            cudaProfilerStop();
+            // the launch covers step l_top .. l (tails ride along): algorithmic work = their forward records
+            long long recs = 0, stmts = 0;
+            for (int32_t q = l; q <= l_top; ++q) { recs += s.step_recs[q]; stmts += s.level_first[q + 1] - s.level_first[q]; }
+            char line[160];
+            snprintf(line, sizeof line, "rev step %d stmts %lld recs %lld dirs %lld grid %u %u tails %d", int(l_top), stmts, recs,
+                     (long long)n_dirs, fgrid.x, fgrid.y, Bi.n_tail);
+            s.prof_log.push_back(line);
+          }
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           nl[i] += 1;
           continue;
@@ -1190,9 +1328,9 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
   CK(cudaSetDevice(s.dev));
   const int64_t D = d_hi - d_lo;
   s.kev_used = 0;
+  s.pev_used = 0;
+  s.sweep_launches = 0;
   CK(cudaEventRecord(s.ev[0], s.stream));
-  CK(cudaEventRecord(s.ev[2], s.stream));
-  CK(cudaEventRecord(s.ev[3], s.stream));
   s.stat["n_passes"] = 0;
   // tapes whose gradient list fits shared memory: one CTA per 32/64 directions walks all steps by itself
   if (D > 0 && c->opt_smallg && s.have_levels && c->opt_schedule != 1 && s.max_step_width < (int64_t(1) << 20)) {
@@ -1231,7 +1369,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       G.ref_block = c->opt_ref_block;
       const size_t smem = need(dc);
       const unsigned grid = unsigned((D + dc - 1) / dc);
-      CK(cudaEventRecord(s.ev[2], s.stream));
+      RET(mark_pass(s));
       if (c->opt_time_kernels) RET(mark(s));
       if (mode == 0) {
         CK(cudaFuncSetAttribute(smallg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1241,8 +1379,9 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
         smallg_kernel<true><<<grid, 512, smem, s.stream>>>(G);
       }
       if (c->opt_time_kernels) RET(mark(s));
-      CK(cudaEventRecord(s.ev[3], s.stream));
+      RET(mark_pass(s));
       s.launches += 1;
+      s.sweep_launches += 1;
       s.stat["pass_dirs"] = double(D);
       s.stat["n_passes"] = 1;
       s.stat["used_schedule"] = 3.0;   // level schedule, shared-memory-resident gradients
@@ -1299,15 +1438,18 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     }
     for (int64_t d0 = d_lo; d0 < d_hi; d0 += pass) {
       const int64_t n = std::min(pass, d_hi - d0);
-      const bool last = d0 + pass >= d_hi;
       CK(cudaMemsetAsync(g, 0, size_t(n_rows) * size_t(K) * 8, s.stream));
       if (sparse) CK(cudaMemsetAsync(s.rowact.p, 0, size_t(n_rows) * size_t(ncb_pass), s.stream));
       seed_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(g, K, seed_slots_dev, d0, int(n),
                                                                     sparse ? s.rowact.as<uint8_t>() : nullptr, ncb_pass, 32 * V);
       s.launches += 1;
-      if (last) CK(cudaEventRecord(s.ev[2], s.stream));
-      RET(launch_sweep(c, s, mode, g, K, n, plan, fused));
-      if (last) CK(cudaEventRecord(s.ev[3], s.stream));
+      RET(mark_pass(s));
+      {
+        const double l0 = s.launches;
+        RET(launch_sweep(c, s, mode, g, K, n, plan, fused));
+        s.sweep_launches += s.launches - l0;
+      }
+      RET(mark_pass(s));
       const dim3 eg(unsigned((n + 31) / 32), unsigned((n_out + 31) / 32));
       extract_kernel<<<eg, dim3(32, 8), 0, s.stream>>>(g, K, out_rows_dev, n_out, int(n), d0 - d_base, out,
                                                         stride_i, stride_d, fused ? s.rowact.as<uint8_t>() : nullptr,
@@ -1333,8 +1475,13 @@ int shard_finish(Shard& s) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
   s.stat["replay_ms"] = ms;                       // zero-fill + seed + sweep + extraction, all passes
-  CK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
-  s.stat["sweep_ms"] = ms;                        // the replay kernels of the LAST pass alone
+  double sweep = 0;
+  for (size_t k = 0; k + 1 < s.pev_used; k += 2) {
+    CK(cudaEventElapsedTime(&ms, s.pev[k], s.pev[k + 1]));
+    sweep += ms;
+  }
+  s.stat["sweep_ms"] = sweep;                     // the replay kernels alone, summed over all passes
+  s.stat["sweep_launches"] = s.sweep_launches;    // their launch count
   // dominant kernel (forward: replay_forward_kernel, reverse: reverse_target_kernel / replay_reverse_kernel),
   // every launch timed on its own when "time_kernels" is on
   double dom = 0, dq[4] = {0, 0, 0, 0};
@@ -1343,6 +1490,14 @@ int shard_finish(Shard& s) {
     CK(cudaEventElapsedTime(&ms, s.kev[k], s.kev[k + 1]));
     dom += ms;
     dq[std::min<size_t>(3, (k / 2) * 4 / std::max<size_t>(n_dom, 1))] += ms;   // by quarter of the sweep, in issue order
+  }
+  if (!s.prof_log.empty()) {   // option "profile_every": which launches the profiler saw, in order
+    if (const char* f = getenv("ADEPT_CUDA_PROFILE_LOG"))
+      if (FILE* fp = fopen(f, "a")) {
+        for (const std::string& l : s.prof_log) fprintf(fp, "%s\n", l.c_str());
+        fclose(fp);
+      }
+    s.prof_log.clear();
   }
   s.stat["dominant_ms"] = dom;
   for (int q = 0; q < 4; ++q) s.stat[std::string("dominant_q") + char('1' + q) + "_ms"] = dq[q];
@@ -1409,17 +1564,22 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
   std::string* errp = &c->err;
   if (mode != ADEPT_CUDA_FORWARD && mode != ADEPT_CUDA_REVERSE) return fail(errp, ADEPT_CUDA_ERR_ARG, "mode must be 0 or 1");
   Shard& root = c->sh[0];
+  const bool is_root_proc = (c->rank0 == 0);
+  // pre-checks first, agreed between the ranks of a one-process-per-GPU job BEFORE anybody enters a collective
+  const int pre = [&]() -> int {
   if (!root.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
   // reference pre-check (adept/jacobian.cpp:208-210, :466-468)
   if (n_indep <= 0 || n_dep <= 0)
     return fail(errp, ADEPT_CUDA_ERR_NOT_IDENTIFIED, "dependent or independent variables not identified");
   if (!indep || !dep) return fail(errp, ADEPT_CUDA_ERR_ARG, "null index list");
-  const bool is_root_proc = (c->rank0 == 0);
   if (is_root_proc && !jac_out) return fail(errp, ADEPT_CUDA_ERR_ARG, "null output");
   for (int64_t i = 0; i < n_indep; ++i)
     if (indep[i] < 0 || indep[i] >= root.max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "independent slot out of range");
   for (int64_t i = 0; i < n_dep; ++i)
     if (dep[i] < 0 || dep[i] >= root.max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "dependent slot out of range");
+  return over_shards(c, [&](size_t k) -> int { return ensure_schedule(c, c->sh[k]); });   // built on first need
+  }();
+  RET(agree(c, pre));
   // offset defaulting exactly as adept/jacobian.cpp:215-220
   if (dep_offset <= 0) dep_offset = n_indep;
   if (indep_offset <= 0) indep_offset = n_dep;
@@ -1478,9 +1638,43 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
       c->stat["d2h_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
   } else {
-    // multi GPU: every rank fills a direction-major block dm[(d-lo)*n_out + i]; the blocks are
+    if (!c->multi_process && !out_on_device && compact_user) {
+      // one process, host output in one of the two compact layouts: every device extracts its block of directions
+      // in the FINAL layout and copies it straight into the caller's buffer over its own PCIe link -- no gather
+      // through device 0, no re-layout pass
+      RET(over_shards(c, [&](size_t k) -> int {
+        Shard& s = c->sh[k];
+        std::string* errp = &s.err;
+        const int64_t lo = lo_of(int(k)), hi = lo_of(int(k) + 1), nd = hi - lo;
+        CK(cudaSetDevice(s.dev));
+        if (nd <= 0) { s.stat["replay_ms"] = 0; s.stat["sweep_ms"] = 0; return 0; }
+        RET(ensure(errp, s.out, size_t(nd) * size_t(n_out) * 8));
+        const int64_t si = dm_is_final ? 1 : nd, sd = dm_is_final ? n_out : 1;
+        RET(shard_enqueue(c, s, mode, s.seed_slots.as<int32_t>(), s.out_slots.as<int32_t>(), n_out, lo, hi, lo,
+                          s.out.as<double>(), si, sd));
+        if (dm_is_final)
+          CK(cudaMemcpyAsync(jac_out + lo * n_out, s.out.p, size_t(nd) * n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+        else
+          CK(cudaMemcpy2DAsync(jac_out + lo, size_t(D) * 8, s.out.p, size_t(nd) * 8, size_t(nd) * 8, size_t(n_out),
+                               cudaMemcpyDeviceToHost, s.stream));
+        return shard_finish(s);
+      }));
+      c->stat["d2h_ms"] = 0.0;   // overlapped with the other devices' sweeps
+      double replay_ms = 0, sweep_ms = 0;
+      for (Shard& s : c->sh) {
+        replay_ms = std::max(replay_ms, s.stat["replay_ms"]);
+        sweep_ms = std::max(sweep_ms, s.stat["sweep_ms"]);
+      }
+      for (const auto& kv : root.stat) c->stat[kv.first] = kv.second;
+      c->stat["replay_ms"] = replay_ms;
+      c->stat["sweep_ms"] = sweep_ms;
+      c->stat["jacobian_wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+      c->stat["kernel_launches"] = c->total_launches();
+      return 0;
+    }
+    // multi GPU, general case: every rank fills a direction-major block dm[(d-lo)*n_out + i]; the blocks are
     // gathered on global rank 0 (ncclSend/ncclRecv over NVLink) and re-laid out there.
-    RET(over_shards(c, [&](size_t k) -> int {
+    const int enq = over_shards(c, [&](size_t k) -> int {
       Shard& s = c->sh[k];
       std::string* errp = &s.err;
       const int r = c->rank0 + int(k);
@@ -1490,22 +1684,28 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
       RET(ensure(errp, s.out, size_t(is_root ? D : std::max<int64_t>(hi - lo, 1)) * size_t(n_out) * 8));
       return shard_enqueue(c, s, mode, s.seed_slots.as<int32_t>(), s.out_slots.as<int32_t>(), n_out, lo, hi,
                            is_root ? 0 : lo, s.out.as<double>(), 1, n_out);
-    }));
-    NK(ncclGroupStart());
-    for (size_t k = 0; k < c->sh.size(); ++k) {
-      Shard& s = c->sh[k];
-      const int r = c->rank0 + int(k);
-      if (r == 0) {
-        for (int q = 1; q < W; ++q) {
-          const int64_t lo = lo_of(q), hi = lo_of(q + 1);
-          if (hi > lo) NK(ncclRecv(s.out.as<double>() + lo * n_out, size_t(hi - lo) * n_out, ncclDouble, q, s.comm, s.stream));
+    });
+    RET(agree(c, enq));   // nobody enters the gather unless everybody can
+    {
+      ncclResult_t nr = ncclSuccess;
+      NKG(nr, ncclGroupStart());
+      for (size_t k = 0; k < c->sh.size(); ++k) {
+        Shard& s = c->sh[k];
+        const int r = c->rank0 + int(k);
+        if (r == 0) {
+          for (int q = 1; q < W; ++q) {
+            const int64_t lo = lo_of(q), hi = lo_of(q + 1);
+            if (hi > lo)
+              NKG(nr, ncclRecv(s.out.as<double>() + lo * n_out, size_t(hi - lo) * n_out, ncclDouble, q, s.comm, s.stream));
+          }
+        } else {
+          const int64_t lo = lo_of(r), hi = lo_of(r + 1);
+          if (hi > lo) NKG(nr, ncclSend(s.out.as<double>(), size_t(hi - lo) * n_out, ncclDouble, 0, s.comm, s.stream));
         }
-      } else {
-        const int64_t lo = lo_of(r), hi = lo_of(r + 1);
-        if (hi > lo) NK(ncclSend(s.out.as<double>(), size_t(hi - lo) * n_out, ncclDouble, 0, s.comm, s.stream));
       }
+      NKG(nr, ncclGroupEnd());
+      if (nr != ncclSuccess) return fail(errp, ADEPT_CUDA_ERR_NCCL, "gather of the Jacobian blocks failed: %s", ncclGetErrorString(nr));
     }
-    NK(ncclGroupEnd());
     RET(over_shards(c, [&](size_t k) -> int { return shard_finish(c->sh[k]); }));
     if (is_root_proc) {
       Shard& s = root;
@@ -1567,6 +1767,7 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
   if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
   if (!gradient_host) return fail(errp, ADEPT_CUDA_ERR_ARG, "null gradient vector");
   CK(cudaSetDevice(s.dev));
+  if (int rc = ensure_schedule(c, s)) { c->err = s.err; return rc; }
   const int64_t G = s.max_gradient;
   double* g = gradient_host;   // device-resident gradient vector: swept in place
   if (!on_device) {
@@ -1603,10 +1804,12 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
                                                                                                kLongThreshold, g);
             s.launches += 1;
           }
-          while (lf < s.long_stmts.size() && s.long_stmts[lf].level == l) {
-            const LongStmt& L = s.long_stmts[lf++];
-            sweep1_forward_long_kernel<<<1, 512, 0, s.stream>>>(recs, L.b, L.e, g);
+          size_t le = lf;
+          while (le < s.long_stmts.size() && s.long_stmts[le].level == l) ++le;
+          if (le > lf) {   // one CTA per long statement of this step
+            sweep1_forward_long_kernel<<<unsigned(le - lf), 512, 0, s.stream>>>(recs, s.long_tab.as<int64_t>() + 2 * lf, g);
             s.launches += 1;
+            lf = le;
           }
         }
       } else {
@@ -1646,7 +1849,7 @@ int init_shard(Shard& s, int dev) {
   s.dev = dev;
   CK(cudaSetDevice(dev));
   CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&s.ev[k]));
+  for (int k = 0; k < 2; ++k) CK(cudaEventCreate(&s.ev[k]));
   CK(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
@@ -1660,15 +1863,16 @@ int init_shard(Shard& s, int dev) {
 void free_shard(Shard& s) {
   cudaSetDevice(s.dev);
   for (Buf* b : {&s.stmt, &s.mult, &s.idx, &s.fwd_t, &s.rev_t, &s.one_chunk, &s.level, &s.fwd_l, &s.fwd_chunk,
-                 &s.foff, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.pos_in_sched, &s.ftgt, &s.fchunk, &s.fpar, &s.out_rows, &s.done, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch})
+                 &s.foff, &s.long_tab, &s.sched_lhs, &s.tgt, &s.tchunk, &s.goff, &s.pos_in_sched, &s.ftgt, &s.fchunk, &s.fpar, &s.out_rows, &s.done, &s.d_level_first, &s.d_step_tchunk, &s.d_step_group, &s.sg_fwd_info, &s.sg_rev_info, &s.abuf, &s.rowact, &s.aflag, &s.a1, &s.g, &s.seed_slots, &s.out_slots, &s.out, &s.g1, &s.scratch, &s.agree_buf})
     release(*b);
   for (int k = 0; k < 2; ++k) {
     if (s.stage[k]) cudaFreeHost(s.stage[k]);
     if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
   }
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < 2; ++k)
     if (s.ev[k]) cudaEventDestroy(s.ev[k]);
   for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
+  for (cudaEvent_t e : s.pev) cudaEventDestroy(e);
   for (cudaEvent_t e : s.aux_ev) cudaEventDestroy(e);
   for (cudaStream_t st : s.aux) cudaStreamDestroy(st);
   if (s.fork_ev) cudaEventDestroy(s.fork_ev);
@@ -1767,7 +1971,7 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   Shard& s = c->sh[0];
   CK(cudaSetDevice(s.dev));
   auto t0 = std::chrono::steady_clock::now();
-  s.have_tape = false;
+  for (Shard& d : c->sh) { d.have_tape = false; d.have_schedule = false; }
   RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
   RET(ensure(errp, s.mult, size_t(n_ops) * 8));
   RET(ensure(errp, s.idx, size_t(n_ops) * 4));
@@ -1781,6 +1985,8 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   s.n_stmt = n_stmt;
   s.n_ops = n_ops;
   s.max_gradient = max_gradient;
+  s.have_tape = true;
+  c->epoch = epoch;
   auto t1 = std::chrono::steady_clock::now();
   c->stat["upload_ms"] = std::chrono::duration<double, std::milli>(t1 - t0).count();
   // single-process multi-GPU: broadcast right away
@@ -1793,33 +1999,29 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
       RET(ensure(errp, d.idx, size_t(n_ops) * 4));
       d.n_stmt = n_stmt; d.n_ops = n_ops; d.max_gradient = max_gradient;
     }
-    NK(ncclGroupStart());
+    ncclResult_t nr = ncclSuccess;
+    NKG(nr, ncclGroupStart());
     for (Shard& d : c->sh) {
-      NK(ncclBroadcast(d.stmt.p, d.stmt.p, size_t(n_stmt) * 8, ncclChar, 0, d.comm, d.stream));
-      NK(ncclBroadcast(d.mult.p, d.mult.p, size_t(n_ops) * 8, ncclChar, 0, d.comm, d.stream));
-      NK(ncclBroadcast(d.idx.p, d.idx.p, size_t(n_ops) * 4, ncclChar, 0, d.comm, d.stream));
+      NKG(nr, ncclBroadcast(d.stmt.p, d.stmt.p, size_t(n_stmt) * 8, ncclChar, 0, d.comm, d.stream));
+      NKG(nr, ncclBroadcast(d.mult.p, d.mult.p, size_t(n_ops) * 8, ncclChar, 0, d.comm, d.stream));
+      NKG(nr, ncclBroadcast(d.idx.p, d.idx.p, size_t(n_ops) * 4, ncclChar, 0, d.comm, d.stream));
     }
-    NK(ncclGroupEnd());
-    for (Shard& d : c->sh) { CK(cudaSetDevice(d.dev)); CK(cudaStreamSynchronize(d.stream)); }
+    NKG(nr, ncclGroupEnd());
+    if (nr != ncclSuccess) return fail(errp, ADEPT_CUDA_ERR_NCCL, "tape broadcast failed: %s", ncclGetErrorString(nr));
+    for (Shard& d : c->sh) { CK(cudaSetDevice(d.dev)); CK(cudaStreamSynchronize(d.stream)); d.have_tape = true; }
     c->stat["bcast_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
   }
-  auto t2 = std::chrono::steady_clock::now();
-  RET(over_shards(c, [&](size_t k) -> int {
-    Shard& d = c->sh[k];
-    std::string* errp = &d.err;
-    RET(build_schedule(c, d));
-    CK(cudaStreamSynchronize(d.stream));
-    d.have_tape = true;
-    return 0;
-  }));
-  c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
-  c->stat["n_levels"] = s.n_levels;
-  c->stat["n_chunks"] = double(s.n_chunks);
-  c->stat["n_records"] = double(s.R);
-  c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
-  c->stat["kernel_launches"] = c->total_launches();
-  for (const char* k : {"an_window_ms", "an_forward_ms", "an_target_ms"}) c->stat[k] = s.stat[k];
-  c->epoch = epoch;
+  // One-process-per-GPU job: the schedule is built by adept_cuda_share_tape on all ranks at once (or on first use).
+  // Otherwise: now, every local shard on its own host thread.
+  if (!c->multi_process) {
+    auto t2 = std::chrono::steady_clock::now();
+    RET(over_shards(c, [&](size_t k) -> int { return ensure_schedule(c, c->sh[k]); }));
+    c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
+    publish_schedule_stats(c);
+    c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
+  } else {
+    c->stat["analysis_ms"] = 0.0;
+  }
   c->stat["upload_total_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return 0;
 }
@@ -1828,43 +2030,48 @@ int adept_cuda_share_tape(adept_cuda_ctx* c, int root_rank) {
   if (!c) return ADEPT_CUDA_ERR_ARG;
   std::string* errp = &c->err;
   if (!c->multi_process) return 0;  // single-process contexts broadcast inside upload_tape
+  if (root_rank < 0 || root_rank >= c->world) return fail(errp, ADEPT_CUDA_ERR_ARG, "root_rank out of range");
   Shard& s = c->sh[0];
   CK(cudaSetDevice(s.dev));
   auto t0 = std::chrono::steady_clock::now();
+  const bool is_root = (c->rank0 == root_rank);
+  // header first: {status, n_stmt, n_ops, max_gradient, epoch}.  A root without a tape says so in the header,
+  // so that its peers (already inside the broadcast) leave with the same error instead of waiting for arrays.
   RET(ensure(errp, s.scratch, 64));
-  int64_t hdr[4] = {s.n_stmt, s.n_ops, s.max_gradient, int64_t(c->epoch)};
-  if (c->rank0 == root_rank) {
-    if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "root has no tape to share");
-    CK(cudaMemcpyAsync(s.scratch.p, hdr, sizeof hdr, cudaMemcpyHostToDevice, s.stream));
-  }
+  int64_t hdr[5] = {is_root && !s.have_tape ? int64_t(ADEPT_CUDA_ERR_NO_TAPE) : 0, s.n_stmt, s.n_ops, s.max_gradient,
+                    int64_t(c->epoch)};
+  if (is_root) CK(cudaMemcpyAsync(s.scratch.p, hdr, sizeof hdr, cudaMemcpyHostToDevice, s.stream));
   NK(ncclBroadcast(s.scratch.p, s.scratch.p, sizeof hdr, ncclChar, root_rank, s.comm, s.stream));
   CK(cudaMemcpyAsync(hdr, s.scratch.p, sizeof hdr, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  if (c->rank0 != root_rank) {
+  if (hdr[0]) return fail(errp, int(hdr[0]), "rank %d has no tape to share", root_rank);
+  int rc = 0;
+  if (!is_root) {
     s.have_tape = false;
-    s.n_stmt = hdr[0]; s.n_ops = hdr[1]; s.max_gradient = hdr[2]; c->epoch = uint64_t(hdr[3]);
-    RET(ensure(errp, s.stmt, size_t(s.n_stmt) * 8));
-    RET(ensure(errp, s.mult, size_t(s.n_ops) * 8));
-    RET(ensure(errp, s.idx, size_t(s.n_ops) * 4));
+    s.have_schedule = false;
+    s.n_stmt = hdr[1]; s.n_ops = hdr[2]; s.max_gradient = hdr[3]; c->epoch = uint64_t(hdr[4]);
+    rc = ensure(errp, s.stmt, size_t(s.n_stmt) * 8);
+    if (!rc) rc = ensure(errp, s.mult, size_t(s.n_ops) * 8);
+    if (!rc) rc = ensure(errp, s.idx, size_t(s.n_ops) * 4);
   }
-  NK(ncclGroupStart());
-  NK(ncclBroadcast(s.stmt.p, s.stmt.p, size_t(s.n_stmt) * 8, ncclChar, root_rank, s.comm, s.stream));
-  NK(ncclBroadcast(s.mult.p, s.mult.p, size_t(s.n_ops) * 8, ncclChar, root_rank, s.comm, s.stream));
-  NK(ncclBroadcast(s.idx.p, s.idx.p, size_t(s.n_ops) * 4, ncclChar, root_rank, s.comm, s.stream));
-  NK(ncclGroupEnd());
+  RET(agree(c, rc));   // an allocation that failed on one rank must not leave the others in the broadcast
+  ncclResult_t nr = ncclSuccess;
+  NKG(nr, ncclGroupStart());
+  NKG(nr, ncclBroadcast(s.stmt.p, s.stmt.p, size_t(s.n_stmt) * 8, ncclChar, root_rank, s.comm, s.stream));
+  NKG(nr, ncclBroadcast(s.mult.p, s.mult.p, size_t(s.n_ops) * 8, ncclChar, root_rank, s.comm, s.stream));
+  NKG(nr, ncclBroadcast(s.idx.p, s.idx.p, size_t(s.n_ops) * 4, ncclChar, root_rank, s.comm, s.stream));
+  NKG(nr, ncclGroupEnd());
+  if (nr != ncclSuccess) return fail(errp, ADEPT_CUDA_ERR_NCCL, "tape broadcast failed: %s", ncclGetErrorString(nr));
   CK(cudaStreamSynchronize(s.stream));
+  s.have_tape = true;
   c->stat["bcast_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (c->rank0 != root_rank) {
-    auto t2 = std::chrono::steady_clock::now();
-    if (int rc = build_schedule(c, s)) { c->err = s.err; return rc; }
-    CK(cudaStreamSynchronize(s.stream));
-    s.have_tape = true;
-    c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
-    c->stat["n_levels"] = s.n_levels;
-    c->stat["n_chunks"] = double(s.n_chunks);
-    c->stat["n_records"] = double(s.R);
-    c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
-  }
+  // every rank analyses its copy NOW, at the same time (the root did not do it in upload_tape)
+  auto t2 = std::chrono::steady_clock::now();
+  rc = ensure_schedule(c, s);
+  if (rc) c->err = s.err;
+  RET(agree(c, rc));   // e.g. a malformed tape: refused by every rank alike
+  publish_schedule_stats(c);
+  c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
   return 0;
 }
 
@@ -1936,6 +2143,7 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
     CK(cudaSetDevice(s.dev));
     // the shared structure replaces whatever tape this context held
     s.have_tape = false;
+    s.have_schedule = false;
     s.have_levels = false;
     s.have_tape_streams = false;
     RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
@@ -2057,6 +2265,9 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "profile_every") {
+    if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "profile_every must be >= 0");
+    c->opt_profile_every = int(value);
   } else if (k == "cbs") {
     if (value < 0 || value > kFusedCbs) return fail(errp, ADEPT_CUDA_ERR_ARG, "cbs must be in 0..32");
     c->opt_cbs = int(value);
@@ -2092,6 +2303,7 @@ int adept_cuda_get_levels(adept_cuda_ctx* c, int32_t* level_out, int64_t n_stmt)
   std::string* errp = &c->err;
   Shard& s = c->sh[0];
   if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
+  if (int rc = ensure_schedule(c, s)) { c->err = s.err; return rc; }
   if (!s.have_levels) return fail(errp, ADEPT_CUDA_ERR_ARG, "no level schedule was built for this tape");
   if (n_stmt != s.n_stmt) return fail(errp, ADEPT_CUDA_ERR_ARG, "n_stmt mismatch");
   CK(cudaSetDevice(s.dev));

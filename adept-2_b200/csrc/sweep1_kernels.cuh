@@ -58,10 +58,12 @@ __global__ void sweep1_target_kernel(const Rec* __restrict__ tgt, const int64_t*
 // rounded on its own, exactly as the reference does without FMA), then one thread adds them
 // in tape order -- the only order that reproduces the reference's bits.
 constexpr int kLongTile = 4096;
-__global__ void __launch_bounds__(512) sweep1_forward_long_kernel(const Rec* __restrict__ recs, int64_t b, int64_t e,
-                                                                   double* g) {
+// One CTA per long statement of the step: range[2*blockIdx.x] = {b, e} of its records.
+__global__ void __launch_bounds__(512) sweep1_forward_long_kernel(const Rec* __restrict__ recs,
+                                                                   const int64_t* __restrict__ range, double* g) {
   __shared__ double prod[kLongTile];
   __shared__ double acc_s;
+  const int64_t b = range[2 * blockIdx.x], e = range[2 * blockIdx.x + 1];
   if (threadIdx.x == 0) acc_s = 0.0;
   __syncthreads();
   for (int64_t t0 = b; t0 < e - 1; t0 += kLongTile) {
@@ -81,15 +83,21 @@ __global__ void __launch_bounds__(512) sweep1_forward_long_kernel(const Rec* __r
   if (threadIdx.x == 0) g[recs[e - 1].slot] = acc_s;
 }
 
-// list long statements of the schedule: out[atomic++] = j
+// list long statements of the schedule: out[3*k] = {j, first record, end record}, k = atomic++ (the count keeps
+// running past max_out so that the host can size a second attempt)
 __global__ void find_long_kernel(const int64_t* __restrict__ foff, int64_t S, int64_t long_threshold,
                                  int64_t* __restrict__ out, int* __restrict__ count, int max_out) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t j = t; j < S; j += stride) {
-    if (foff[j + 1] - foff[j] > long_threshold) {
+    const int64_t b = foff[j], e = foff[j + 1];
+    if (e - b > long_threshold) {
       const int k = atomicAdd(count, 1);
-      if (k < max_out) out[k] = j;
+      if (k < max_out) {
+        out[3 * k] = j;
+        out[3 * k + 1] = b;
+        out[3 * k + 2] = e;
+      }
     }
   }
 }

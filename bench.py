@@ -5,23 +5,29 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1, one rank per GPU)
 
 A "step" is one pass of the hot path over one batch of synthetic input: one whole Jacobian of the
-workload's tape.  Default workload (N = 1): BASELINE config 2 -- Toon advection nx=4096, 1000
-time steps (8 195 096 statements / 36 858 096 operations / 12 287 slots), 4096x4096 Jacobian by
-REVERSE sweeps on B200s.  With N > 1 the directions of the same Jacobian are
-partitioned over the ranks: tape ncclBroadcast from rank 0, result blocks gathered on rank 0
-(total work fixed => "scaling": "strong").
+workload's tape.  Default workload: BASELINE config 4 at FULL size -- the configuration the metric is
+quoted on ("at 1/2/4/8 B200", the HBM-bound one): seeded random tape of 1e8
+statements / 4.0e8 operations / 2^20 slots, 8192x8192 Jacobian, by FORWARD sweeps (what Stack::jacobian
+dispatches to for a square Jacobian, include/adept/Stack.h:374-385); the REVERSE sweep of the same tape
+is measured in the same run and printed under "reverse".  With N > 1 the directions of the same Jacobian
+are partitioned over the ranks: tape ncclBroadcast from rank 0, every rank analyses its copy at the same
+time, result blocks gathered on rank 0 (total work fixed => "scaling": "strong").
 
 One JSON line on rank 0:
   value        whole-job op*dir/s with the tape and its schedule already resident in HBM when the timed
                region starts (what the reference times around stack_.jacobian(), differentiator.h:338-348);
                the timed region holds zero-fill + seeding + sweep + extraction (+ NCCL gather).
   e2e          the same metric through the C-ABI call a user makes, with HOST buffers: pinned H2D of the
-               tape (+ device-side schedule construction) and D2H of the Jacobian inside the timed region.
-  roofline     dominant replay kernel: ALGORITHMIC bytes per launch / its CUDA-event launch time, against
-               the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-  cpu_baseline the reference's own OpenMP Stack::jacobian_reverse (oracle/_ref, built from the unmodified
-               reference) on this box's host cores, on a bounded sample of the same Jacobian's rows.
---impl reference prints the reference's CPU arm as the main line instead.
+               tape (+ broadcast + device-side schedule construction) and D2H of the Jacobian inside the
+               timed region.
+  roofline     dominant replay kernel: ALGORITHMIC bytes per launch / its average launch duration, both from
+               the TIMED REGION ITSELF (CUDA events around the replay kernels of every pass on the engine's
+               own stream, production launch mode: PDL on, same streams), against the measured HBM copy
+               bandwidth (MEASURED_PEAKS.json).  "traffic" = DRAM bytes per launch from the committed ncu
+               capture of the same workload (profiles/traffic.json), when there is one.
+  cpu_baseline the reference's own OpenMP Stack::jacobian_* (oracle/_ref, built from the unmodified
+               reference) on this box's host cores, on a bounded sample of the same Jacobian's directions.
+--impl reference prints the reference's CPU arm as the main line instead (same config keys).
 """
 from __future__ import annotations
 
@@ -47,16 +53,19 @@ WORKLOADS = {
     # name: (description, tape builder, mode)
     "toon4096": dict(desc="BASELINE config 2: Toon advection nx=4096 nt=1000 (8195096 stmts / 36858096 ops / 12287 slots), "
                           "4096x4096 Jacobian, reverse sweeps", scheme="toon", nx=4096, nt=1000, mode=1),
+    "synthetic1e6_fwd": dict(desc="BASELINE config 4 at 1/100 length (smoke runs): seeded random tape, 1e6 statements, 2^16 slots, "
+                                  "1024x1024 Jacobian, forward sweeps", scheme="synthetic", n=1_000_000, log2_slots=16, n_io=1024,
+                             mode=0, also_reverse=True),
     "toon1024": dict(desc="reduced config 2: Toon advection nx=1024 nt=250, 1024x1024 Jacobian, reverse sweeps",
                      scheme="toon", nx=1024, nt=250, mode=1),
     "lw100": dict(desc="BASELINE config 1: Lax-Wendroff nx=100 nt=2000, 100x100 Jacobian, forward sweeps",
                   scheme="lw", nx=100, nt=2000, mode=0),
     "synthetic1e7_fwd": dict(desc="BASELINE config 4 at 1/10 length: seeded random tape, 1e7 statements (mean 4 operands), "
                                   "2^20 slots, 8192x8192 Jacobian, forward sweeps", scheme="synthetic", n=10_000_000,
-                             log2_slots=20, n_io=8192, mode=0),
+                             log2_slots=20, n_io=8192, mode=0, also_reverse=True),
     "synthetic1e8_fwd": dict(desc="BASELINE config 4, full size: seeded random tape, 1e8 statements (mean 4 operands), "
                                   "2^20 slots, 8192x8192 Jacobian, forward sweeps", scheme="synthetic", n=100_000_000,
-                             log2_slots=20, n_io=8192, mode=0),
+                             log2_slots=20, n_io=8192, mode=0, also_reverse=True),
     "synthetic1e8_rev": dict(desc="BASELINE config 4, full size: seeded random tape, 1e8 statements (mean 4 operands), "
                                   "2^20 slots, 8192x8192 Jacobian, reverse sweeps", scheme="synthetic", n=100_000_000,
                              log2_slots=20, n_io=8192, mode=1),
@@ -148,7 +157,7 @@ def reference_rate(tape, mode, target_seconds=12.0, variant=None):
     if po.ref_available(variant):
         rt = po.RefTape(variant)
         P = rt.packet_size
-        threads = po._ref(variant).ref_max_threads()
+        threads = host_cores()      # set_max_jacobian_threads(0) = omp_get_num_procs() threads (adept/Stack.cpp:101-104)
         rt.inject(tape["stmt"], tape["mult"], tape["idx"], tape["max_gradient"] - 1, tape["indep"], tape["dep"])
 
         def run(dirs):
@@ -160,7 +169,7 @@ def reference_rate(tape, mode, target_seconds=12.0, variant=None):
             return rt.last_seconds
     else:   # the restatement, if the compiled reference did not travel
         kind = "port"
-        P, threads = 8, os.cpu_count() or 1
+        P, threads = 8, host_cores()
 
         def run(dirs):
             ind = tape["indep"][:dirs] if mode == 0 else tape["indep"]
@@ -266,15 +275,61 @@ def side_workload(args, name):
     return 0
 
 
+def shared_config(wl, S, O, G, D, mode, world, dirs_note=""):
+    """The workload description, identical (keys and values) for our arm and for --impl reference."""
+    return {"workload": wl["desc"] + dirs_note, "statements": int(S), "operations": int(O), "slots": int(G),
+            "directions": int(D), "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))      # what omp_get_num_procs() reports
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_main(args, wl, mode, W, K):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: the unmodified
+    Stack::jacobian_forward/_reverse under OpenMP) on all host cores, each step a bounded sample of the workload."""
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())      # torchrun exports OMP_NUM_THREADS=1
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    tape = build_tape(wl)
+    S, O, G = tape["stmt"].shape[0] - 1, tape["idx"].size, tape["max_gradient"]
+    D_all = tape["dep"].size if mode else tape["indep"].size
+    # the whole --steps K --warmup W run should end within a few minutes: ~150 s of sweeps in all
+    per_step = min(8.0, max(0.5, 150.0 / (K + min(W, 3))))
+    r = reference_rate(tape, mode, target_seconds=per_step)
+    for _ in range(min(W, 3)):
+        r["run"](min(r["dirs"], r["threads"] * r["P"]))
+    ts = [r["run"](r["dirs"]) for _ in range(K)]
+    t = sum(ts) / K
+    value = O * r["dirs"] / t
+    sample = (f"{r['dirs']} of {D_all} directions ({'rows' if mode else 'columns'}) of the same Jacobian per step; "
+              f"rate is linear in blocks (adept/jacobian.cpp:146-147); build {r['variant']} P={r['P']} -O3 -ffp-contract=off; "
+              f"OpenMP threads = {r['threads']} (all host cores)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": shared_config(wl, S, O, G, D_all, mode, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="toon4096", choices=sorted(WORKLOADS) + ["rosenbrock1e7", "ensemble1e5"])
+    ap.add_argument("--workload", default="synthetic1e8_fwd", choices=sorted(WORKLOADS) + ["rosenbrock1e7", "ensemble1e5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--reverse-steps", type=int, default=2, help="timed steps of the other sweep direction (workloads that name it)")
+    ap.add_argument("--time-kernels", type=int, default=0, help="cross-check: one extra step with every launch bracketed by events "
+                                                                 "(single stream, PDL off: a different, slower execution mode)")
     ap.add_argument("--schedule", type=int, default=0)
     ap.add_argument("--pass-dirs", type=int, default=0)
     ap.add_argument("--window", type=int, default=0)
@@ -286,44 +341,24 @@ def main():
     ap.add_argument("--cbs", type=int, default=0, help="fused kernel: column blocks per CTA (0 = automatic)")
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch between the per-step kernels")
     ap.add_argument("--tail", type=int, default=1, help="fused kernel: tiny steps ride along with the previous launch")
+    ap.add_argument("--opt", action="append", default=[], help="extra engine option key=value (repeatable)")
     ap.add_argument("--dirs", type=int, default=0,
                     help="EXPERIMENT ONLY: sweep just the first N directions (what one rank of a multi-GPU run holds); "
                          "the line is then not the named workload and says so in config")
     args = ap.parse_args()
-    if args.workload in ("rosenbrock1e7", "ensemble1e5"):
-        return side_workload(args, args.workload) if int(os.environ.get("RANK", "0")) == 0 else 0
-    W = max(args.warmup, 3)
-    K = max(args.steps, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in ("rosenbrock1e7", "ensemble1e5"):
+        return side_workload(args, args.workload) if rank == 0 else 0
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
     wl = WORKLOADS[args.workload]
     mode = wl["mode"]
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        tape = build_tape(wl)
-        S, O = tape["stmt"].shape[0] - 1, tape["idx"].size
-        r = reference_rate(tape, mode, target_seconds=8.0)
-        for _ in range(W):
-            r["run"](min(r["dirs"], r["threads"] * r["P"]))
-        ts = [r["run"](r["dirs"]) for _ in range(K)]
-        t = sum(ts) / K
-        value = O * r["dirs"] / t
-        sample = (f"{r['dirs']} of {tape['dep'].size if mode else tape['indep'].size} directions "
-                  f"({'rows' if mode else 'columns'}) of the same Jacobian per step; rate is linear in blocks "
-                  f"(adept/jacobian.cpp:146-147); build {r['variant']} P={r['P']} -O3 -ffp-contract=off")
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-            "warmup": W, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "statements": S, "operations": O},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
-        return 0
+        return reference_main(args, wl, mode, W, K) if rank == 0 else 0
 
     # ------------------------------------------------------------------ our arm
     import torch
@@ -332,7 +367,8 @@ def main():
     pkg = importlib.import_module("adept-2_b200")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))
     eng = pkg.Engine([local_rank])
     if world > 1:
         ids = [eng.unique_id() if rank == 0 else None]
@@ -350,6 +386,9 @@ def main():
     eng.set_option("pdl", args.pdl)
     if args.streams:
         eng.set_option("streams", args.streams)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
 
     def barrier():
         torch.cuda.synchronize()
@@ -357,7 +396,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    t_gen = time.perf_counter()
     tape = build_tape(wl) if rank == 0 else None
+    t_gen = time.perf_counter() - t_gen
     meta = [None]
     if rank == 0:
         meta = [dict(S=int(tape["stmt"].shape[0] - 1), O=int(tape["idx"].size), G=int(tape["max_gradient"]),
@@ -366,23 +413,13 @@ def main():
         dist.broadcast_object_list(meta, src=0)
     m = meta[0]
     S, O, G = m["S"], m["O"], m["G"]
-    indep, dep = m["indep"], m["dep"]
-    if args.dirs > 0:   # experiment: a rank's share of the directions
-        if mode == 0:
-            indep = np.ascontiguousarray(indep[:args.dirs])
-        else:
-            dep = np.ascontiguousarray(dep[:args.dirs])
-    N, M = indep.size, dep.size
-    D = N if mode == 0 else M
-    work = float(O) * D
+    indep_all, dep_all = m["indep"], m["dep"]
 
     # pinned host copies of the tape (what a Stack shim would hand over) and of the result
     if rank == 0:
         pin = {k: torch.from_numpy(np.ascontiguousarray(tape[k])).pin_memory() for k in ("stmt", "mult", "idx")}
         host = {k: v.numpy() for k, v in pin.items()}
-        out_pin = torch.empty(N * M, dtype=torch.float64).pin_memory()
-    h2d = (S + 1) * 8 + O * 12 + (N + M) * 4
-    d2h = N * M * 8
+        out_pin = torch.empty(indep_all.size * dep_all.size, dtype=torch.float64).pin_memory()
 
     def upload():
         if rank == 0:
@@ -391,46 +428,111 @@ def main():
             eng.share_tape(0)
 
     upload()
-    out_dev = torch.empty(N * M, dtype=torch.float64, device="cuda") if rank == 0 else None
+    out_dev = torch.empty(indep_all.size * dep_all.size, dtype=torch.float64, device="cuda") if rank == 0 else None
     out_ptr = out_dev.data_ptr() if rank == 0 else 0
+    peak, peak_src = peaks()
 
-    def step():
-        eng.jacobian_device(mode, indep, dep, out_ptr)   # collective when world > 1
-        return eng.stat("replay_ms", 0.0)
+    def measure(mode, n_warm, n_steps, with_clocks):
+        """W untimed + K timed Jacobians of one sweep direction, tape and schedule resident.  Everything reported
+        comes from the timed region itself: wall clock between barriers, and the engine's CUDA events around each
+        step (replay_ms) and around the replay kernels of every pass (sweep_ms) on its own stream."""
+        indep, dep = indep_all, dep_all
+        if args.dirs > 0:   # experiment: a rank's share of the directions
+            if mode == 0:
+                indep = np.ascontiguousarray(indep[:args.dirs])
+            else:
+                dep = np.ascontiguousarray(dep[:args.dirs])
+        N, M = indep.size, dep.size
+        D = N if mode == 0 else M
+        work = float(O) * D
 
-    for _ in range(W):
-        step()
-    launches0 = eng.stat("kernel_launches", 0.0)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t0 = time.perf_counter()
-    ev_ms = 0.0
-    for _ in range(K):
-        ev_ms += step()
-    barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.stat("kernel_launches", 0.0) - launches0
-    wall = torch.tensor([t1 - t0, ev_ms / 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-    wall_s, ev_s = float(wall[0]), float(wall[1])
-    value = work * K / wall_s
+        def step():
+            eng.jacobian_device(mode, indep, dep, out_ptr)   # collective when world > 1
+            return eng.stat("replay_ms", 0.0), eng.stat("sweep_ms", 0.0), eng.stat("sweep_launches", 0.0)
 
-    host_issue_ms = eng.stat("host_issue_ms", None)   # host time spent enqueueing the last timed sweep's launches
-    # dominant kernel, every launch bracketed by CUDA events on its own stream (one extra step)
-    eng.set_option("time_kernels", 1)
-    step()
-    dom_ms, dom_launches = eng.stat("dominant_ms", 0.0), eng.stat("dominant_launches", 0.0)
-    dom_quarters = [eng.stat(f"dominant_q{q}_ms", None) for q in (1, 2, 3, 4)]
-    sweep_ms = eng.stat("sweep_ms", 0.0)
-    used = eng.stat("used_schedule", 0.0)
-    used_fused = bool(eng.stat("used_fused", 0.0)) and used == 2 and mode == 1
-    eng.set_option("time_kernels", 0)
+        for _ in range(n_warm):
+            step()
+        launches0 = eng.stat("kernel_launches", 0.0)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0 and with_clocks:
+            sampler.start()
+        t0 = time.perf_counter()
+        ev_ms = sw_ms = sw_launches = 0.0
+        for _ in range(n_steps):
+            a, b, c = step()
+            ev_ms += a
+            sw_ms += b
+            sw_launches += c
+        barrier()
+        t1 = time.perf_counter()
+        clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+        launches = eng.stat("kernel_launches", 0.0) - launches0
+        wall_s, ev_s, sw_s = allmax([t1 - t0, ev_ms / 1e3, sw_ms / 1e3])
+        used = eng.stat("used_schedule", 0.0)
+        used_fused = bool(eng.stat("used_fused", 0.0)) and used == 2 and mode == 1
+        n_passes = max(1.0, eng.stat("n_passes", 1.0) or 1.0)
+        kname = {(1, 2.0): "reverse_target_kernel<2>", (0, 2.0): "forward_level_kernel<2,sparse>", (1, 1.0): "replay_reverse_kernel",
+                 (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
+        if used_fused:
+            kname[(1, 2.0)] = "reverse_fused_kernel<2>"
+        bpo = alg_bytes_per_opdir(S, O, mode)
+        # algorithmic bytes of this rank's share of the step (SURVEY.md 8d); the two-kernel reverse form splits them
+        # between the snapshot kernel (per-statement part) and the gather (per-operation part): the events bracket both
+        step_bytes = bpo * work / world
+        n_l = sw_launches / n_steps if n_steps else 0.0
+        n_streams = max(1.0, eng.stat("sweep_streams", 1.0) or 1.0)
+        roof = None
+        if sw_s > 0 and n_l > 0:
+            sweep_s = sw_s / n_steps                  # replay kernels of one Jacobian, max over ranks
+            ach = step_bytes / sweep_s / 1e9
+            roof = {"bound": "hbm", "kernel": kname.get((mode, used), "?"), "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": n_l, "algorithmic_bytes_per_launch": step_bytes / n_l,
+                    "avg_launch_us": 1e6 * sweep_s * n_streams / n_l, "concurrent_streams": n_streams,
+                    "sweep_ms_per_step": 1e3 * sweep_s,
+                    "source": "CUDA events of the timed region itself (engine stream, PDL and streams as in production), "
+                              "around the replay kernels of every pass; zero-fill, seeding and extraction are outside them "
+                              "but inside ms_per_step",
+                    "frac_of_whole_step": step_bytes / (wall_s / n_steps) / 1e9 / peak,
+                    "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
+                            "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}
+            try:   # DRAM traffic per launch from the committed ncu capture of this workload, when there is one
+                key = args.workload if mode == wl["mode"] else args.workload.replace("_fwd", "_rev")
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+                if tr and tr.get("kernel") == roof["kernel"]:
+                    roof["traffic"] = tr["dram_bytes_per_launch"]
+                    roof["traffic_sample"] = tr["launch"]
+                    if tr.get("algorithmic_bytes_per_launch"):
+                        roof["traffic_over_algorithmic"] = tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"]
+            except Exception:
+                pass
+        engine_info = {"schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
+                       "fused_reverse": used_fused, "steps_in_schedule": eng.stat("n_levels", 0),
+                       "pass_dirs": eng.stat("pass_dirs", 0), "n_passes": n_passes,
+                       "host_issue_ms": eng.stat("host_issue_ms", None),
+                       "l2": "inputs larger than L2: record stream %.0f MB + workspace %.0f MB per pass" %
+                             (16e-6 * (O + S), 8e-6 * G * (2 if used_fused else 1) * min(D, eng.stat("pass_dirs", D) or D))}
+        return dict(N=N, M=M, D=D, work=work, wall_s=wall_s, ev_s=ev_s, value=work * n_steps / wall_s, launches=launches,
+                    clocks=clocks, roof=roof, engine=engine_info, indep=indep, dep=dep, used=used, used_fused=used_fused)
 
-    # end to end through the C-ABI with host buffers: H2D of the tape + schedule build + replay + D2H
+    main_m = measure(mode, W, K, True)
+    N, M, D, work = main_m["N"], main_m["M"], main_m["D"], main_m["work"]
+    indep, dep = main_m["indep"], main_m["dep"]
+    h2d = (S + 1) * 8 + O * 12 + (N + M) * 4
+    d2h = N * M * 8
+
+    # cross-check only (NOT the source of roofline): every launch bracketed by events, one stream, PDL off
+    xcheck = None
+    if args.time_kernels:
+        eng.set_option("time_kernels", 1)
+        eng.jacobian_device(mode, indep, dep, out_ptr)
+        xcheck = {"dominant_ms": eng.stat("dominant_ms", 0.0), "dominant_launches": eng.stat("dominant_launches", 0.0),
+                  "ms_by_quarter_of_sweep": [eng.stat(f"dominant_q{q}_ms", None) for q in (1, 2, 3, 4)],
+                  "note": "single stream, PDL off: slower than the timed region by construction"}
+        eng.set_option("time_kernels", 0)
+
+    # end to end through the C-ABI with host buffers: H2D of the tape (+ broadcast) + schedule build + replay + D2H
     barrier()
     e2e_s = None
     phases = {}
@@ -455,73 +557,49 @@ def main():
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
         phases["upload_call_ms"] = 1e3 * t_up / args.e2e_steps
         phases["jacobian_call_ms"] = 1e3 * t_jac / args.e2e_steps
-        for k in ("upload_ms", "analysis_ms", "an_window_ms", "an_forward_ms", "an_target_ms", "an_fused_ms", "bcast_ms", "replay_ms",
-                  "d2h_ms", "jacobian_wall_ms", "upload_total_ms"):
+        for k in ("upload_ms", "bcast_ms", "analysis_ms", "an_validate_ms", "an_window_ms", "an_pack_ms", "an_forward_ms", "an_target_ms",
+                  "an_fused_ms", "replay_ms", "d2h_ms", "jacobian_wall_ms", "upload_total_ms"):
             phases[k] = eng.stat(k, None)
-        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_s = float(e2e_t[0])
+        e2e_s = allmax([e2e_s])[0]
+
+    # rows/columns for the parity spot check below, taken now (the next measurement reuses the output buffers)
+    sub = np.linspace(0, D - 1, 8).astype(np.int32)
+    got = None
+    if rank == 0:
+        if args.e2e_steps > 0:
+            full = out_pin.numpy()[:N * M].reshape(N, M)
+        else:
+            full = out_dev[:N * M].reshape(N, M)
+        got = full[sub, :] if mode == 0 else full[:, sub]
+        got = np.ascontiguousarray(got.cpu().numpy() if hasattr(got, "cpu") else got)
+
+    # the other sweep direction of the same tape (config 4 names both), a short timed region of its own
+    other = None
+    if wl.get("also_reverse") and args.reverse_steps > 0 and args.dirs == 0:
+        om = measure(1 - mode, 1, args.reverse_steps, False)
+        other = {"value": om["value"], "unit": UNIT, "steps": args.reverse_steps, "warmup": 1,
+                 "ms_per_step": 1e3 * om["wall_s"] / args.reverse_steps, "roofline": om["roof"], "engine": om["engine"],
+                 "algorithmic_bytes_per_opdir": alg_bytes_per_opdir(S, O, 1 - mode), "gpu_launches": int(om["launches"]),
+                 "an_fused_ms": eng.stat("an_fused_ms", None)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # parity spot check inside the bench (checker only): a few rows against the oracle, bit for bit
+    # parity spot check inside the bench (checker only): a few directions against the oracle, bit for bit
+    # (full-matrix and full-size parity live in tests/: test_gpu_parity.py, test_gpu_fullsize.py)
     parity = None
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as po
-        sub = np.linspace(0, D - 1, 8).astype(np.int32)
         ind = indep[sub] if mode == 0 else indep
         dp = dep if mode == 0 else dep[sub]
         rc, want = po.jacobian(tape["stmt"], tape["mult"], tape["idx"], G, ind, dp, mode, n_threads=0)
-        if not args.e2e_steps:   # nothing was copied to the host yet
-            out_pin.copy_(out_dev)
-            torch.cuda.synchronize()
-        full = out_pin.numpy().reshape(N, M)
-        got = full[sub, :] if mode == 0 else full[:, sub]
-        parity = bool(rc == 0 and np.array_equal(np.ascontiguousarray(got).ravel().view(np.uint64), want.view(np.uint64)))
+        parity = bool(rc == 0 and np.array_equal(got.ravel().view(np.uint64), want.view(np.uint64)))
     except Exception as e:  # the bench number does not depend on the checker being present
         parity = f"not checked: {e}"
 
-    peak, peak_src = peaks()
-    bpo = alg_bytes_per_opdir(S, O, mode)
-    # algorithmic bytes of the dominant kernel: the per-operation part (reverse: 16 B, forward: 8 B per op*dir;
-    # the per-statement part belongs to the snapshot kernel / the TAIL stores); the fused reverse kernel does the
-    # per-statement part too, so it is credited with the whole formula
-    dom_bytes = 16.0 * work / world if used == 2 and mode == 1 and not used_fused else bpo * work / world
-    roof = None
-    n_passes = max(1.0, eng.stat("n_passes", 1.0) or 1.0)
-    pass_dirs = eng.stat("pass_dirs", 0.0) or float(D)
-    d_rank = float(D) / world
-    last_pass_share = max(0.0, d_rank - (n_passes - 1.0) * pass_dirs) / d_rank if n_passes > 1 else 1.0
-    if dom_ms and dom_launches:
-        ach = dom_bytes / (dom_ms / 1e3) / 1e9
-        kname = {(1, 2.0): "reverse_target_kernel<2>", (0, 2.0): "forward_level_kernel<2,sparse>", (1, 1.0): "replay_reverse_kernel",
-                 (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
-        if used_fused:
-            kname[(1, 2.0)] = "reverse_fused_kernel<2>"
-        roof = {"bound": "hbm", "kernel": kname.get((mode, used), "?"),
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "launches_per_step": dom_launches,
-                "algorithmic_bytes_per_launch": dom_bytes / dom_launches,
-                "avg_launch_us": 1e3 * dom_ms / dom_launches,
-                "ms_by_quarter_of_sweep": dom_quarters,
-                # sweep_ms covers the LAST pass only: credit it with that pass's share of the directions
-                "whole_sweep_frac": (bpo * work / world * last_pass_share) / (sweep_ms / 1e3) / 1e9 / peak if sweep_ms else None,
-                "note": "gradient working set per pass is G*K*8 B; when it fits the 126 MB L2 the fraction is an "
-                        "effective bandwidth and may exceed DRAM traffic (SURVEY.md 8d caveat)"}
-
-    if roof is not None:
-        try:   # DRAM traffic of one profiled launch (ncu --set full), when a capture for this workload is on file
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            if tr and tr.get("kernel") == roof["kernel"]:
-                roof["traffic"] = tr["dram_bytes_per_launch"]
-                roof["traffic_sample"] = tr["launch"]
-        except Exception:
-            pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -534,24 +612,23 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * wall_s / K, "ms_per_step_cuda_events": 1e3 * ev_s / K,
+        "metric": METRIC, "value": main_m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * main_m["wall_s"] / K, "ms_per_step_cuda_events": 1e3 * main_m["ev_s"] / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"] + (f" -- EXPERIMENT: first {args.dirs} directions only" if args.dirs > 0 else ""),
-                   "statements": S, "operations": O, "slots": G, "directions": D,
-                   "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}",
-                   "schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
-                   "steps_in_schedule": eng.stat("n_levels", 0), "pass_dirs": eng.stat("pass_dirs", 0),
-                   "n_passes": eng.stat("n_passes", 0), "host_issue_ms": host_issue_ms,
-                   "l2": "inputs larger than L2: tape streams %.0f MB + workspace %.0f MB per step" %
-                         (16e-6 * (O + S), 8e-6 * G * min(D, eng.stat("pass_dirs", D) or D))},
-        "clocks": clocks,
+        "config": shared_config(wl, S, O, G, D, mode, world,
+                                f" -- EXPERIMENT: first {args.dirs} directions only" if args.dirs > 0 else ""),
+        "engine": main_m["engine"],
+        "clocks": main_m["clocks"],
         "e2e": {"value": (work / e2e_s) if e2e_s else None, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s if e2e_s else None, "phases_ms": phases},
-        "gpu_launches": int(launches),
-        "roofline": roof,
+        "gpu_launches": int(main_m["launches"]),
+        "roofline": main_m["roof"],
+        "algorithmic_bytes_per_opdir": alg_bytes_per_opdir(S, O, mode),
+        "reverse" if mode == 0 else "forward": other,
+        "time_kernels_cross_check": xcheck,
         "cpu_baseline": cpu,
         "parity_bit_exact_vs_oracle": parity,
+        "tape_generation_s": round(t_gen, 1),
     }
     print(json.dumps(line))
     if world > 1:

@@ -47,3 +47,48 @@ def test_single_process_multi_device(pkg, po, ndev):
             assert same_bits(eng.jacobian(mode, t["indep"], t["dep"]), want)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_ensemble_members_sharded_over_devices(pkg, po, ndev):
+    """BASELINE config 3's partition: ensemble members are block-sharded over the devices, no
+    collective at all; every member's Jacobian must equal the oracle's for that member's tape."""
+    if _ndev() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    eng = pkg.Engine(list(range(ndev)))
+    try:
+        t = pkg.tapegen.radiance_tape()
+        for B in (ndev - 1, 1003):        # fewer members than devices (idle shards), and a ragged split
+            rng = np.random.default_rng(B)
+            mm = t["mult"][:, None] * (1.0 + 0.05 * rng.standard_normal((t["mult"].size, B)))
+            for mode in (1, 0):
+                got = eng.jacobian_batch(mode, t["stmt"], t["idx"], t["max_gradient"], mm, t["indep"], t["dep"])
+                assert got.shape == (B, t["indep"].size, t["dep"].size) and not np.isnan(got).any()
+                for b in sorted(set([0, B - 1, B // 2] + list(rng.integers(0, B, 16)))):
+                    rc, want = po.jacobian(t["stmt"], np.ascontiguousarray(mm[:, b]), t["idx"], t["max_gradient"],
+                                           t["indep"], t["dep"], mode)
+                    assert rc == 0 and same_bits(got[b], want), (B, mode, b)
+    finally:
+        eng.close()
+
+
+def test_direct_d2h_layouts(pkg, po):
+    """One process, several devices, host output: in the two compact layouts every device copies its block of
+    directions straight into the caller's buffer (no gather through device 0); any other stride goes through the
+    NCCL gather + re-layout.  All must give the reference's bits."""
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    eng = pkg.Engine([0, 1])
+    try:
+        t = pkg.tapegen.advection_tape("toon", 192, 30)
+        n = m = 192
+        eng.upload_tape(t["stmt"], t["mult"], t["idx"], t["max_gradient"])
+        for mode in (0, 1):
+            for do, io in ((1, 0), (0, 1), (n, 1), (1, m), (1, m + 3)):
+                size = 1 + (m - 1) * (do if do > 0 else n) + (n - 1) * (io if io > 0 else m)
+                got = eng.jacobian(mode, t["indep"], t["dep"], out=np.full(size, np.nan), dep_offset=do, indep_offset=io)
+                rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], mode,
+                                       dep_offset=do, indep_offset=io, out=np.full(size, np.nan), n_threads=0)
+                assert rc == 0 and same_bits(got, want), (mode, do, io)
+    finally:
+        eng.close()

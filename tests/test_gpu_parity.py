@@ -336,7 +336,7 @@ def test_synthetic_config4_shape(engine, po, pkg):
 
 
 # ---- size-independent properties at a size the oracle would not finish quickly ------------------------
-def test_large_advection_properties(engine, pkg):
+def test_large_advection_properties(engine, po, pkg):
     """NX=1024, nt=300 (1.06e6 statements), too big for a quick oracle run: size-independent properties.
     Toon: forward == reverse to rounding (the reference's own criterion, test/test_thread_safe.cpp:86-113)
     and level schedule == tape order, bit for bit.  Lax-Wendroff (a stable scheme: the Toon recurrence
@@ -353,6 +353,12 @@ def test_large_advection_properties(engine, pkg):
     assert same_bits(jo, jf[sub])
     jo = engine.jacobian(1, t["indep"], t["dep"][sub]).reshape(1024, 64)
     assert same_bits(jo, jr[:, sub])
+    # ... and both against the ORACLE on a subset of directions (not only against this engine's other kernel)
+    sub = np.arange(3, 1024, 64).astype(np.int32)
+    rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"][sub], t["dep"], 0, n_threads=0)
+    assert rc == 0 and same_bits(np.ascontiguousarray(jf[sub]), want)
+    rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"][sub], 1, n_threads=0)
+    assert rc == 0 and same_bits(np.ascontiguousarray(jr[:, sub]), want)
 
     t = pkg.tapegen.advection_tape("lw", 1024, 300)
     upload(engine, t, LEVELS)
