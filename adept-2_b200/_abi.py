@@ -38,6 +38,9 @@ SIGNATURES = {
     "adept_cuda_adjoint_device": (C.c_int, [_vp, _vp, C.c_int]),
     "adept_cuda_jacobian_batch": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64,
                                             _vp, _i64, _vp, _i64, _vp]),
+    "adept_cuda_chain_begin": (C.c_int, [_vp, _i64, _vp]),
+    "adept_cuda_chain_push": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64]),
+    "adept_cuda_chain_end": (C.c_int, [_vp, _vp]),
     "adept_cuda_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "adept_cuda_get_stat": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
     "adept_cuda_get_levels": (C.c_int, [_vp, _vp, _i64]),

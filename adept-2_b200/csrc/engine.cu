@@ -11,6 +11,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -122,8 +125,47 @@ struct Shard {
 
 }  // namespace
 
+namespace {
+// Checkpoint-chained replay (reference test/test_checkpoint.cpp:166-225): a sequence of tapes, each
+// swept ONCE in reverse, the gradients at block k's inputs becoming the seeds at block k+1's outputs.  The caller
+// re-records into the same host arrays right after a push, so a push copies the block into one of two pinned host
+// slots and returns; a worker thread moves it to one of two DEVICE tape slots (copy stream), builds the schedule,
+// seeds from the device-resident hand-off vector, sweeps and gathers the next hand-off -- while the caller records
+// the next block.  The upload of block k+1 is issued before the worker waits for the sweep of block k.
+struct ChainBlock {
+  int slot = 0;
+  int64_t n_stmt = 0, n_ops = 0, max_gradient = 0, n_seed = 0, n_out = 0;
+  bool seed_from_handoff = false;
+  bool uploaded = false;   // its H2D has already been issued (pipelined behind the previous block's sweep)
+};
+struct ChainHostSlot {
+  void* p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stmt, mult, idx, seed slots, seed values, out slots
+  size_t cap[6] = {0, 0, 0, 0, 0, 0};
+  bool busy = false;
+};
+struct Chain {
+  bool active = false;
+  int64_t n_handoff = 0;
+  Buf handoff, owner;
+  Buf dtape[2][3], dseed_slots[2], dseed_vals[2], dout_slots[2];
+  ChainHostSlot hs[2];
+  cudaStream_t copy = nullptr;
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<ChainBlock> q;
+  bool stop = false;
+  int rc = 0;
+  std::string err;
+  int64_t blocks = 0;
+  double busy_ms = 0, sweep_ms = 0, analysis_ms = 0;
+};
+}  // namespace
+
 struct adept_cuda_ctx {
   std::vector<Shard> sh;
+  Chain chain;
   int world = 1;       // total ranks (devices over all processes)
   int rank0 = 0;       // global rank of sh[0]
   bool multi_process = false;
@@ -1564,6 +1606,7 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
   std::string* errp = &c->err;
   if (mode != ADEPT_CUDA_FORWARD && mode != ADEPT_CUDA_REVERSE) return fail(errp, ADEPT_CUDA_ERR_ARG, "mode must be 0 or 1");
   Shard& root = c->sh[0];
+  if (c->chain.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "a checkpoint chain is open on this context (adept_cuda_chain_end first)");
   const bool is_root_proc = (c->rank0 == 0);
   // pre-checks first, agreed between the ranks of a one-process-per-GPU job BEFORE anybody enters a collective
   const int pre = [&]() -> int {
@@ -1758,11 +1801,75 @@ int do_jacobian(adept_cuda_ctx* c, int mode, const int32_t* indep, int64_t n_ind
 }
 
 
-// single-direction sweep on shard 0: gradient vector in/out on the host
+// Enqueue (no host synchronisation) one single-direction sweep of the device vector g[max_gradient] on the
+// shard's stream.  adjoint: Stack::compute_adjoint (adept/Stack.cpp:139-164), else compute_tangent_linear (:170-190).
+int enqueue_sweep1(adept_cuda_ctx* c, Shard& s, int adjoint, double* g, int flags, bool* ordered_out) {
+  std::string* errp = &s.err;
+  const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
+  if (ordered_out) *ordered_out = ordered;
+  if (s.R <= 0) return 0;
+  if (ordered) {
+    RET(ensure_tape_streams(s));
+    ReplayArgs A{};
+    A.g = g;
+    A.K = 1;
+    A.n_colblocks = 1;
+    A.n_dirs = 1;  // K = 1: lanes 1..31 are masked off
+    A.ref_block = 1;
+    A.recs = (adjoint ? s.rev_t : s.fwd_t).as<Rec>();
+    A.chunk_begin = s.one_chunk.as<int64_t>();
+    A.first_chunk = 0;
+    if (adjoint) replay_reverse_kernel<false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
+    else replay_forward_kernel<true, false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
+    s.launches += 1;
+  } else {
+    const Rec* recs = s.fwd_l.as<Rec>();
+    const int64_t* foff = s.foff.as<int64_t>();
+    if (!adjoint) {
+      size_t lf = 0;  // cursor into long_stmts (sorted by schedule position, hence by step)
+      for (int32_t l = 1; l <= s.n_levels; ++l) {
+        const int64_t j0 = s.level_first[l], j1 = s.level_first[l + 1];
+        if (j1 > j0) {
+          sweep1_forward_level_kernel<<<unsigned((j1 - j0 + 255) / 256), 256, 0, s.stream>>>(recs, foff, j0, j1,
+                                                                                             kLongThreshold, g);
+          s.launches += 1;
+        }
+        size_t le = lf;
+        while (le < s.long_stmts.size() && s.long_stmts[le].level == l) ++le;
+        if (le > lf) {   // one CTA per long statement of this step
+          sweep1_forward_long_kernel<<<unsigned(le - lf), 512, 0, s.stream>>>(recs, s.long_tab.as<int64_t>() + 2 * lf, g);
+          s.launches += 1;
+          lf = le;
+        }
+      }
+    } else {
+      RET(ensure_target_stream(c, s));
+      RET(ensure(errp, s.a1, size_t(std::max<int64_t>(s.max_step_width, 1)) * 8));
+      for (int32_t l = s.n_levels; l >= 1; --l) {
+        const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
+        if (n <= 0) continue;
+        sweep1_snapshot_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(s.sched_lhs.as<int32_t>(), j0, n, g,
+                                                                                s.a1.as<double>());
+        s.launches += 1;
+        const int64_t g0 = s.step_group[l], g1 = s.step_group[l + 1];
+        if (g1 > g0) {
+          sweep1_target_kernel<<<unsigned((g1 - g0 + 255) / 256), 256, 0, s.stream>>>(
+              s.tgt.as<Rec>(), s.goff.as<int64_t>(), g0, g1, g, s.a1.as<double>());
+          s.launches += 1;
+        }
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// single-direction sweep on shard 0: gradient vector in/out on the host (or in place on the device)
 int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initialized, int flags, bool on_device = false) {
   if (!c) return ADEPT_CUDA_ERR_ARG;
   std::string* errp = &c->err;
   Shard& s = c->sh[0];
+  if (c->chain.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "a checkpoint chain is open on this context (adept_cuda_chain_end first)");
   if (!initialized) return fail(errp, ADEPT_CUDA_ERR_GRAD_NOT_INIT, "gradients not initialized");
   if (!s.have_tape) return fail(errp, ADEPT_CUDA_ERR_NO_TAPE, "no tape uploaded");
   if (!gradient_host) return fail(errp, ADEPT_CUDA_ERR_ARG, "null gradient vector");
@@ -1776,61 +1883,8 @@ int do_sweep1(adept_cuda_ctx* c, int adjoint, double* gradient_host, int initial
     if (int rc = upload(s, g, gradient_host, size_t(G) * 8)) { c->err = s.err; return rc; }
   }
   CK(cudaEventRecord(s.ev[0], s.stream));
-  const bool ordered = (flags & ADEPT_CUDA_SWEEP_ORDERED) || !s.have_levels || c->opt_schedule == 1;
-  if (s.R > 0) {
-    if (ordered) {
-      if (int rc = ensure_tape_streams(s)) { c->err = s.err; return rc; }
-      ReplayArgs A{};
-      A.g = g;
-      A.K = 1;
-      A.n_colblocks = 1;
-      A.n_dirs = 1;  // K = 1: lanes 1..31 are masked off
-      A.ref_block = 1;
-      A.recs = (adjoint ? s.rev_t : s.fwd_t).as<Rec>();
-      A.chunk_begin = s.one_chunk.as<int64_t>();
-      A.first_chunk = 0;
-      if (adjoint) replay_reverse_kernel<false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
-      else replay_forward_kernel<true, false><<<dim3(1, 1), 32, 0, s.stream>>>(A);
-      s.launches += 1;
-    } else {
-      const Rec* recs = s.fwd_l.as<Rec>();
-      const int64_t* foff = s.foff.as<int64_t>();
-      if (!adjoint) {
-        size_t lf = 0;  // cursor into long_stmts (sorted by schedule position, hence by step)
-        for (int32_t l = 1; l <= s.n_levels; ++l) {
-          const int64_t j0 = s.level_first[l], j1 = s.level_first[l + 1];
-          if (j1 > j0) {
-            sweep1_forward_level_kernel<<<unsigned((j1 - j0 + 255) / 256), 256, 0, s.stream>>>(recs, foff, j0, j1,
-                                                                                               kLongThreshold, g);
-            s.launches += 1;
-          }
-          size_t le = lf;
-          while (le < s.long_stmts.size() && s.long_stmts[le].level == l) ++le;
-          if (le > lf) {   // one CTA per long statement of this step
-            sweep1_forward_long_kernel<<<unsigned(le - lf), 512, 0, s.stream>>>(recs, s.long_tab.as<int64_t>() + 2 * lf, g);
-            s.launches += 1;
-            lf = le;
-          }
-        }
-      } else {
-        if (int rc = ensure_target_stream(c, s)) { c->err = s.err; return rc; }
-        RET(ensure(errp, s.a1, size_t(std::max<int64_t>(s.max_step_width, 1)) * 8));
-        for (int32_t l = s.n_levels; l >= 1; --l) {
-          const int64_t j0 = s.level_first[l], n = s.level_first[l + 1] - j0;
-          if (n <= 0) continue;
-          sweep1_snapshot_kernel<<<unsigned((n + 255) / 256), 256, 0, s.stream>>>(s.sched_lhs.as<int32_t>(), j0, n, g,
-                                                                                  s.a1.as<double>());
-          s.launches += 1;
-          const int64_t g0 = s.step_group[l], g1 = s.step_group[l + 1];
-          if (g1 > g0) {
-            sweep1_target_kernel<<<unsigned((g1 - g0 + 255) / 256), 256, 0, s.stream>>>(
-                s.tgt.as<Rec>(), s.goff.as<int64_t>(), g0, g1, g, s.a1.as<double>());
-            s.launches += 1;
-          }
-        }
-      }
-    }
-  }
+  bool ordered = false;
+  if (int rc = enqueue_sweep1(c, s, adjoint, g, flags, &ordered)) { c->err = s.err; return rc; }
   CK(cudaEventRecord(s.ev[1], s.stream));
   CK(cudaGetLastError());
   if (!on_device) CK(cudaMemcpyAsync(gradient_host, g, size_t(G) * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -1879,6 +1933,168 @@ void free_shard(Shard& s) {
   for (Buf& b : s.pool) release(b);
   if (s.comm) ncclCommDestroy(s.comm);
   if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// Checkpoint-chained replay
+// ---------------------------------------------------------------------------------------
+// set_gradients semantics (include/adept/Stack.h:290-306): values are stored one after the other, so when a slot is
+// named twice the LAST value wins.  owner[slot] = largest i naming it (atomicMax), then thread i stores iff it owns.
+__global__ void chain_owner_kernel(const int32_t* __restrict__ slots, int64_t n, int32_t* __restrict__ owner) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(&owner[slots[i]], static_cast<int32_t>(i));
+}
+__global__ void chain_scatter_kernel(const int32_t* __restrict__ slots, const double* __restrict__ vals, int64_t n,
+                                     const int32_t* __restrict__ owner, double* __restrict__ g) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && owner[slots[i]] == static_cast<int32_t>(i)) g[slots[i]] = vals[i];
+}
+__global__ void chain_gather_kernel(const int32_t* __restrict__ slots, int64_t n, const double* __restrict__ g,
+                                    double* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = g[slots[i]];
+}
+
+int chain_issue_upload(adept_cuda_ctx* c, ChainBlock& b) {
+  Chain& ch = c->chain;
+  Shard& s = c->sh[0];
+  std::string* errp = &s.err;
+  const int k = b.slot;
+  const size_t bytes[6] = {size_t(b.n_stmt) * 8, size_t(b.n_ops) * 8, size_t(b.n_ops) * 4, size_t(b.n_seed) * 4,
+                           b.seed_from_handoff ? 0 : size_t(b.n_seed) * 8, size_t(b.n_out) * 4};
+  Buf* dst[6] = {&ch.dtape[k][0], &ch.dtape[k][1], &ch.dtape[k][2], &ch.dseed_slots[k], &ch.dseed_vals[k], &ch.dout_slots[k]};
+  for (int a = 0; a < 6; ++a) {
+    RET(ensure(errp, *dst[a], bytes[a]));
+    if (bytes[a]) CK(cudaMemcpyAsync(dst[a]->p, ch.hs[k].p[a], bytes[a], cudaMemcpyHostToDevice, ch.copy));
+  }
+  CK(cudaEventRecord(ch.h2d_done[k], ch.copy));
+  b.uploaded = true;
+  return 0;
+}
+
+// one block on the worker thread: (upload) -> schedule -> seed -> sweep -> gather; the next block's upload is issued
+// before this block's sweep is waited for
+int chain_run_block(adept_cuda_ctx* c, ChainBlock b) {
+  Chain& ch = c->chain;
+  Shard& s = c->sh[0];
+  std::string* errp = &s.err;
+  CK(cudaSetDevice(s.dev));
+  auto t0 = std::chrono::steady_clock::now();
+  if (!b.uploaded) RET(chain_issue_upload(c, b));
+  CK(cudaStreamWaitEvent(s.stream, ch.h2d_done[b.slot], 0));
+  // the shard's tape buffers and this slot's trade places: the previous block's raw arrays are dead (its sweep only
+  // reads the streams derived from them, and those are rebuilt below)
+  std::swap(s.stmt, ch.dtape[b.slot][0]);
+  std::swap(s.mult, ch.dtape[b.slot][1]);
+  std::swap(s.idx, ch.dtape[b.slot][2]);
+  s.n_stmt = b.n_stmt;
+  s.n_ops = b.n_ops;
+  s.max_gradient = b.max_gradient;
+  s.have_tape = true;
+  s.have_schedule = false;
+  auto ta = std::chrono::steady_clock::now();
+  RET(build_schedule(c, s));
+  ch.analysis_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ta).count();
+  const int64_t G = b.max_gradient;
+  RET(ensure(errp, s.g1, size_t(G) * 8));
+  RET(ensure(errp, ch.owner, size_t(G) * 4));
+  double* g = s.g1.as<double>();
+  CK(cudaMemsetAsync(g, 0, size_t(G) * 8, s.stream));                 // initialize_gradients: all zero (adept/Stack.cpp:515-531)
+  CK(cudaMemsetAsync(ch.owner.p, 0xFF, size_t(G) * 4, s.stream));
+  if (b.n_seed > 0) {
+    const unsigned gs = unsigned((b.n_seed + 255) / 256);
+    const int32_t* slots = ch.dseed_slots[b.slot].as<int32_t>();
+    const double* vals = b.seed_from_handoff ? ch.handoff.as<double>() : ch.dseed_vals[b.slot].as<double>();
+    chain_owner_kernel<<<gs, 256, 0, s.stream>>>(slots, b.n_seed, ch.owner.as<int32_t>());
+    chain_scatter_kernel<<<gs, 256, 0, s.stream>>>(slots, vals, b.n_seed, ch.owner.as<int32_t>(), g);
+    s.launches += 2;
+  }
+  CK(cudaEventRecord(s.ev[0], s.stream));
+  RET(enqueue_sweep1(c, s, 1, g, 0, nullptr));
+  CK(cudaEventRecord(s.ev[1], s.stream));
+  chain_gather_kernel<<<unsigned((b.n_out + 255) / 256), 256, 0, s.stream>>>(ch.dout_slots[b.slot].as<int32_t>(), b.n_out, g,
+                                                                            ch.handoff.as<double>());
+  s.launches += 1;
+  CK(cudaGetLastError());
+  {  // the next block, if it is already waiting: start its upload now, behind nothing but the copy engine
+    std::unique_lock<std::mutex> lk(ch.mu);
+    if (!ch.q.empty() && !ch.q.front().uploaded) {
+      ChainBlock& nb = ch.q.front();
+      lk.unlock();          // only this thread pops; the caller only appends
+      RET(chain_issue_upload(c, nb));
+    }
+  }
+  CK(cudaStreamSynchronize(s.stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+  ch.sweep_ms += ms;
+  ch.busy_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  ch.blocks += 1;
+  return 0;
+}
+
+void chain_worker(adept_cuda_ctx* c) {
+  Chain& ch = c->chain;
+  for (;;) {
+    ChainBlock b;
+    {
+      std::unique_lock<std::mutex> lk(ch.mu);
+      ch.cv.wait(lk, [&] { return ch.stop || !ch.q.empty(); });
+      if (ch.q.empty()) return;
+      b = ch.q.front();
+      ch.q.pop_front();
+    }
+    int rc = 0;
+    {
+      std::unique_lock<std::mutex> lk(ch.mu);
+      rc = ch.rc;
+    }
+    if (!rc) {
+      rc = chain_run_block(c, b);
+      if (rc) {
+        std::unique_lock<std::mutex> lk(ch.mu);
+        ch.rc = rc;
+        ch.err = c->sh[0].err;
+      }
+    }
+    {
+      std::unique_lock<std::mutex> lk(ch.mu);
+      ch.hs[b.slot].busy = false;
+    }
+    ch.cv.notify_all();
+  }
+}
+
+void chain_shutdown(adept_cuda_ctx* c) {
+  Chain& ch = c->chain;
+  if (ch.worker.joinable()) {
+    {
+      std::unique_lock<std::mutex> lk(ch.mu);
+      ch.stop = true;
+    }
+    ch.cv.notify_all();
+    ch.worker.join();
+  }
+  ch.stop = false;
+  ch.active = false;
+}
+
+void chain_free(adept_cuda_ctx* c) {
+  chain_shutdown(c);
+  Chain& ch = c->chain;
+  cudaSetDevice(c->sh[0].dev);
+  for (int k = 0; k < 2; ++k) {
+    for (int a = 0; a < 3; ++a) release(ch.dtape[k][a]);
+    release(ch.dseed_slots[k]);
+    release(ch.dseed_vals[k]);
+    release(ch.dout_slots[k]);
+    for (int a = 0; a < 6; ++a)
+      if (ch.hs[k].p[a]) { cudaFreeHost(ch.hs[k].p[a]); ch.hs[k].p[a] = nullptr; ch.hs[k].cap[a] = 0; }
+    if (ch.h2d_done[k]) { cudaEventDestroy(ch.h2d_done[k]); ch.h2d_done[k] = nullptr; }
+  }
+  release(ch.handoff);
+  release(ch.owner);
+  if (ch.copy) { cudaStreamDestroy(ch.copy); ch.copy = nullptr; }
 }
 
 }  // namespace
@@ -1932,6 +2148,7 @@ int adept_cuda_create(adept_cuda_ctx** out, const int* devices, int n_devices) {
 
 void adept_cuda_destroy(adept_cuda_ctx* c) {
   if (!c) return;
+  chain_free(c);
   for (Shard& s : c->sh) free_shard(s);
   delete c;
 }
@@ -1968,6 +2185,7 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   if (!statements || n_stmt < 1 || n_ops < 0 || max_gradient < 1 || (n_ops > 0 && (!multiplier || !index)))
     return fail(errp, ADEPT_CUDA_ERR_ARG, "bad tape arguments");
   if (max_gradient >= (int64_t(1) << 31)) return fail(errp, ADEPT_CUDA_ERR_LIMIT, "max_gradient >= 2^31");
+  if (c->chain.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "a checkpoint chain is open on this context (adept_cuda_chain_end first)");
   Shard& s = c->sh[0];
   CK(cudaSetDevice(s.dev));
   auto t0 = std::chrono::steady_clock::now();
@@ -2235,6 +2453,133 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
   }));
   c->stat["batch_wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   c->stat["kernel_launches"] = c->total_launches();
+  return 0;
+}
+
+int adept_cuda_chain_begin(adept_cuda_ctx* c, int64_t n_handoff, const double* handoff_host) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  if (n_handoff < 1) return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: the hand-off vector needs at least one element");
+  Chain& ch = c->chain;
+  if (ch.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: already open (call adept_cuda_chain_end first)");
+  Shard& s = c->sh[0];
+  CK(cudaSetDevice(s.dev));
+  if (!ch.copy) CK(cudaStreamCreateWithFlags(&ch.copy, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k)
+    if (!ch.h2d_done[k]) CK(cudaEventCreateWithFlags(&ch.h2d_done[k], cudaEventDisableTiming));
+  RET(ensure(errp, ch.handoff, size_t(n_handoff) * 8));
+  if (handoff_host) CK(cudaMemcpy(ch.handoff.p, handoff_host, size_t(n_handoff) * 8, cudaMemcpyHostToDevice));
+  else CK(cudaMemset(ch.handoff.p, 0, size_t(n_handoff) * 8));
+  ch.n_handoff = n_handoff;
+  ch.rc = 0;
+  ch.err.clear();
+  ch.blocks = 0;
+  ch.busy_ms = ch.sweep_ms = ch.analysis_ms = 0;
+  ch.q.clear();
+  ch.hs[0].busy = ch.hs[1].busy = false;
+  ch.stop = false;
+  ch.active = true;
+  ch.worker = std::thread(chain_worker, c);
+  return 0;
+}
+
+int adept_cuda_chain_push(adept_cuda_ctx* c, const void* statements, int64_t n_stmt, const double* multiplier,
+                          const int32_t* index, int64_t n_ops, int64_t max_gradient, const int32_t* seed_slots,
+                          int64_t n_seed, const double* seed_values, const int32_t* out_slots, int64_t n_out) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  Chain& ch = c->chain;
+  if (!ch.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: not open (call adept_cuda_chain_begin first)");
+  if (!statements || n_stmt < 1 || n_ops < 0 || max_gradient < 1 || (n_ops > 0 && (!multiplier || !index)))
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "bad tape arguments");
+  if (max_gradient >= (int64_t(1) << 31)) return fail(errp, ADEPT_CUDA_ERR_LIMIT, "max_gradient >= 2^31");
+  if (n_seed < 0 || (n_seed > 0 && !seed_slots) || !out_slots) return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: null slot list");
+  if (n_out != ch.n_handoff)
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: a block hands %lld gradients on, the chain was opened for %lld", (long long)n_out,
+                (long long)ch.n_handoff);
+  if (!seed_values && n_seed != ch.n_handoff)
+    return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: seeding from the hand-off vector needs n_seed == n_handoff");
+  for (int64_t i = 0; i < n_seed; ++i)
+    if (seed_slots[i] < 0 || seed_slots[i] >= max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "chain: seed slot out of range");
+  for (int64_t i = 0; i < n_out; ++i)
+    if (out_slots[i] < 0 || out_slots[i] >= max_gradient) return fail(errp, ADEPT_CUDA_ERR_RANGE, "chain: output slot out of range");
+  // a free pinned slot (at most two blocks are in flight: one being swept, one waiting or uploading)
+  int k = -1;
+  {
+    std::unique_lock<std::mutex> lk(ch.mu);
+    ch.cv.wait(lk, [&] { return ch.rc != 0 || !ch.hs[0].busy || !ch.hs[1].busy; });
+    if (ch.rc) { c->err = ch.err; return ch.rc; }
+    k = !ch.hs[0].busy ? 0 : 1;
+    ch.hs[k].busy = true;
+  }
+  CK(cudaSetDevice(c->sh[0].dev));
+  const void* src[6] = {statements, multiplier, index, seed_slots, seed_values, out_slots};
+  const size_t bytes[6] = {size_t(n_stmt) * 8, size_t(n_ops) * 8, size_t(n_ops) * 4, size_t(n_seed) * 4,
+                           seed_values ? size_t(n_seed) * 8 : 0, size_t(n_out) * 4};
+  for (int a = 0; a < 6; ++a) {
+    if (!bytes[a]) continue;
+    ChainHostSlot& h = ch.hs[k];
+    if (h.cap[a] < bytes[a]) {
+      if (h.p[a]) CK(cudaFreeHost(h.p[a]));
+      h.p[a] = nullptr;
+      h.cap[a] = 0;
+      const size_t want = bytes[a] + bytes[a] / 4 + 4096;
+      cudaError_t e = cudaMallocHost(&h.p[a], want);
+      if (e != cudaSuccess) {
+        std::unique_lock<std::mutex> lk(ch.mu);
+        h.busy = false;
+        return fail(errp, ADEPT_CUDA_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+      }
+      h.cap[a] = want;
+    }
+    // host copy into the pinned slot, split over a few threads for long tapes (one core moves ~10 GB/s)
+    const int nt = bytes[a] >= (size_t(16) << 20) ? 4 : 1;
+    const size_t part = (bytes[a] + nt - 1) / nt;
+    char* d = static_cast<char*>(h.p[a]);
+    const char* sp = static_cast<const char*>(src[a]);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+      const size_t o = size_t(t) * part;
+      if (o < bytes[a]) th.emplace_back([=]() { std::memcpy(d + o, sp + o, std::min(part, bytes[a] - o)); });
+    }
+    std::memcpy(d, sp, std::min(part, bytes[a]));
+    for (std::thread& t : th) t.join();
+  }
+  ChainBlock b;
+  b.slot = k;
+  b.n_stmt = n_stmt;
+  b.n_ops = n_ops;
+  b.max_gradient = max_gradient;
+  b.n_seed = n_seed;
+  b.n_out = n_out;
+  b.seed_from_handoff = (seed_values == nullptr);
+  {
+    std::unique_lock<std::mutex> lk(ch.mu);
+    ch.q.push_back(b);
+  }
+  ch.cv.notify_all();
+  return 0;
+}
+
+int adept_cuda_chain_end(adept_cuda_ctx* c, double* handoff_host) {
+  if (!c) return ADEPT_CUDA_ERR_ARG;
+  std::string* errp = &c->err;
+  Chain& ch = c->chain;
+  if (!ch.active) return fail(errp, ADEPT_CUDA_ERR_ARG, "chain: not open");
+  {  // drain
+    std::unique_lock<std::mutex> lk(ch.mu);
+    ch.cv.wait(lk, [&] { return ch.q.empty() && !ch.hs[0].busy && !ch.hs[1].busy; });
+  }
+  chain_shutdown(c);
+  c->stat["chain_blocks"] = double(ch.blocks);
+  c->stat["chain_busy_ms"] = ch.busy_ms;
+  c->stat["chain_sweep_ms"] = ch.sweep_ms;
+  c->stat["chain_analysis_ms"] = ch.analysis_ms;
+  c->stat["kernel_launches"] = c->total_launches();
+  c->epoch = 0;
+  if (ch.rc) { c->err = ch.err; return ch.rc; }
+  CK(cudaSetDevice(c->sh[0].dev));
+  if (handoff_host) CK(cudaMemcpy(handoff_host, ch.handoff.p, size_t(ch.n_handoff) * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 

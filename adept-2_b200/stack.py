@@ -169,6 +169,28 @@ class Engine:
         """In-place forward sweep of a device-resident gradient vector."""
         self._chk(self.L.adept_cuda_tangent_linear_device(self.h, C.c_void_p(gradient_ptr), int(flags)))
 
+    # -- checkpoint-chained replay (reference test/test_checkpoint.cpp:166-225) -------------------
+    def chain_begin(self, n_handoff: int, handoff=None):
+        h = None if handoff is None else np.ascontiguousarray(handoff, dtype=np.float64)
+        self._chk(self.L.adept_cuda_chain_begin(self.h, int(n_handoff), _ptr(h)))
+
+    def chain_push(self, stmt, mult, idx, max_gradient, seed_slots, out_slots, seed_values=None):
+        """One block: g = 0; g[seed_slots] = seed_values (None: the device-resident hand-off vector); reverse sweep;
+        hand-off = g[out_slots].  Returns once the block is staged; the arrays may be reused at once."""
+        stmt = np.ascontiguousarray(stmt, dtype=np.int32).reshape(-1, 2)
+        mult = np.ascontiguousarray(mult, dtype=np.float64)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        ss = np.ascontiguousarray(seed_slots, dtype=np.int32)
+        os_ = np.ascontiguousarray(out_slots, dtype=np.int32)
+        sv = None if seed_values is None else np.ascontiguousarray(seed_values, dtype=np.float64)
+        self._chk(self.L.adept_cuda_chain_push(self.h, _ptr(stmt), stmt.shape[0], _ptr(mult), _ptr(idx), idx.shape[0],
+                                               int(max_gradient), _ptr(ss), ss.size, _ptr(sv), _ptr(os_), os_.size))
+
+    def chain_end(self, n_handoff: int):
+        out = np.full(int(n_handoff), np.nan)
+        self._chk(self.L.adept_cuda_chain_end(self.h, _ptr(out)))
+        return out
+
     def jacobian_batch(self, mode, stmt, idx, max_gradient, multipliers, indep, dep):
         """multipliers: float64 [n_ops, n_members].  Returns [n_members, n_indep, n_dep] (each member
         column-major n_dep x n_indep, the reference's default layout)."""

@@ -281,18 +281,26 @@ def shared_config(wl, S, O, G, D, mode, world, dirs_note=""):
             "directions": int(D), "mode": "reverse" if mode else "forward", "parallelism": f"directions/{world}"}
 
 
-def host_cores():
+def _host_cores():
     try:
         return len(os.sched_getaffinity(0))      # what omp_get_num_procs() reports
     except Exception:
         return os.cpu_count() or 1
 
 
+# taken at import, before any OpenMP runtime is loaded: libgomp may bind the initial thread (OMP_PROC_BIND), after
+# which the affinity mask of this process no longer shows the cores the reference's OpenMP loop will use
+_HOST_CORES = _host_cores()
+
+
+def host_cores():
+    return _HOST_CORES
+
+
 def reference_main(args, wl, mode, W, K):
     """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: the unmodified
     Stack::jacobian_forward/_reverse under OpenMP) on all host cores, each step a bounded sample of the workload."""
     os.environ["OMP_NUM_THREADS"] = str(host_cores())      # torchrun exports OMP_NUM_THREADS=1
-    os.environ.setdefault("OMP_PROC_BIND", "spread")
     tape = build_tape(wl)
     S, O, G = tape["stmt"].shape[0] - 1, tape["idx"].size, tape["max_gradient"]
     D_all = tape["dep"].size if mode else tape["indep"].size

@@ -115,6 +115,32 @@ int  adept_cuda_adjoint(adept_cuda_ctx* ctx, double* gradient_host, int initiali
 int  adept_cuda_tangent_linear_device(adept_cuda_ctx* ctx, double* gradient_device, int flags);
 int  adept_cuda_adjoint_device(adept_cuda_ctx* ctx, double* gradient_device, int flags);
 
+/* ---- checkpoint-chained replay ----------------------------------------------------------------
+   reference test/test_checkpoint.cpp:166-225: a long simulation is differentiated block by block, last block first.
+   Per block the user re-records the block (new_recording ... ), seeds the block's OUTPUT variables with the gradients
+   the previous block produced at ITS inputs (adept::set_gradients), calls Stack::reverse() and reads the gradients at
+   the block's inputs (adept::get_gradients): many short tapes, each swept exactly once.  Done call by call through
+   adept_cuda_upload_tape + adept_cuda_adjoint every block pays a blocking upload and two max_gradient-long PCIe copies.
+
+   The chain keeps the hand-off vector (n_handoff doubles) ON THE DEVICE and pipelines the blocks:
+     adept_cuda_chain_begin(ctx, n, h0)   opens a chain; the hand-off vector starts as h0 (NULL: zeros)
+     adept_cuda_chain_push(ctx, tape..., seed_slots, n_seed, seed_values, out_slots, n_out)
+         one block: gradient vector = 0; g[seed_slots[i]] = seed_values[i] (seed_values == NULL: the hand-off vector,
+         n_seed == n_handoff; a slot named twice keeps the LAST value, as set_gradients would); reverse sweep
+         (Stack::compute_adjoint, adept/Stack.cpp:139-164, level-scheduled, same bits); hand-off[i] = g[out_slots[i]]
+         (n_out == n_handoff).  Returns as soon as the block has been copied to a pinned staging slot: the caller may
+         re-record into the same arrays at once.  A worker thread owns the device side: block k+1 is uploaded (own copy
+         stream, second device tape slot) while block k is being swept.  Errors of earlier blocks surface at the next
+         push or at chain_end.
+     adept_cuda_chain_end(ctx, h)         waits for the last block and copies the hand-off vector to h (NULL: discard)
+   No other call may be made on the context while a chain is open. */
+int  adept_cuda_chain_begin(adept_cuda_ctx* ctx, int64_t n_handoff, const double* handoff_host);
+int  adept_cuda_chain_push(adept_cuda_ctx* ctx, const void* statements, int64_t n_stmt,
+                           const double* multiplier, const int32_t* index, int64_t n_ops, int64_t max_gradient,
+                           const int32_t* seed_slots, int64_t n_seed, const double* seed_values,
+                           const int32_t* out_slots, int64_t n_out);
+int  adept_cuda_chain_end(adept_cuda_ctx* ctx, double* handoff_host);
+
 /* Ensemble of B tapes sharing ONE structure (statements, index, indep, dep) with per-member
    multipliers laid out [op][member] (BASELINE config 3: simulate_radiances ensemble).  Output is
    member-major: jac_out[b*n_dep*n_indep + i + j*n_dep] (the reference's default column-major
@@ -156,6 +182,8 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
                      between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
+     "profile_every" N > 0: cudaProfilerStart/Stop around every N-th launch of a level sweep (for
+                     `ncu --profile-from-start off`); the bracketed launches are listed in $ADEPT_CUDA_PROFILE_LOG
 */
 int  adept_cuda_set_option(adept_cuda_ctx* ctx, const char* key, int64_t value);
 

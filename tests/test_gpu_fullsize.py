@@ -40,7 +40,9 @@ def test_toon4096_full_size_rows_against_the_oracle(engine, po, pkg):
         rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"][cols], t["dep"], 0,
                                n_threads=0)
         assert rc == 0 and same_bits(np.ascontiguousarray(jf[cols, :]), want)
-        assert np.sqrt(np.mean((jf - jr) ** 2)) <= 1e-5                              # test/test_thread_safe.cpp:86-113
+        # (no forward-vs-reverse RMSD check here: over 1000 steps the Toon recurrence amplifies the rounding difference
+        # between the two summation orders far beyond the 1e-5 that test/test_thread_safe.cpp:86-113 uses at nt=200;
+        # both sweeps equal the reference's own bits, which is the bar)
     finally:
         _opts(engine)
 

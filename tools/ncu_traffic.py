@@ -59,6 +59,8 @@ def summarise(csv_path, log_path, mode, label=""):
         d[r[imetric]] = float(r[ival].replace(",", ""))
     launches = [per[k] for k in sorted(per)]
     log = [l.split() for l in open(log_path) if l.strip()]
+    if len(log) == 2 * len(launches) and log[:len(launches)] == log[len(launches):]:
+        log = log[:len(launches)]      # the log was flushed twice under ncu (same lines, same order)
     assert len(log) == len(launches), (len(log), len(launches))
     per_rec = 8.0 if mode == 0 else 16.0
     tot_dram = tot_alg = tot_ns = 0.0
