@@ -73,6 +73,7 @@ struct Shard {
   // the tape as recorded
   Buf stmt, mult, idx;
   int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
+  int64_t n_ops_recorded = 0;   // before "remove_null" compaction
   bool have_tape = false;       // the recorded arrays are on this device
   bool have_schedule = false;   // build_schedule has run for them (validation, level analysis, forward stream)
   bool have_tape_streams = false;
@@ -182,6 +183,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_remove_null = 0;    // 1: drop zero-multiplier operations on upload (the reference's ADEPT_REMOVE_NULL_STATEMENTS build)
   int opt_profile_every = 0;  // > 0: cudaProfilerStart/Stop around every Nth launch of a level sweep (ncu --profile-from-start off)
   // stats
   std::map<std::string, double> stat;
@@ -393,19 +395,58 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     return fail(errp, ADEPT_CUDA_ERR_LIMIT, "tape too long: n_ops + n_statements = %lld >= 2^31", (long long)R);
   const int T = 256;
   auto tp = std::chrono::steady_clock::now();
-  // 1. validate (a bad slot would otherwise be a wild device access)
+  // 1. validate (a bad slot would otherwise be a wild device access); multiplier statistics on the way
   RET(ensure(errp, s.scratch, 64));
   CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
   validate_kernel<<<grid_for(std::max(O, s.n_stmt), T, s.sm_count), T, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), s.mult.as<double>(), O, s.max_gradient, s.scratch.as<int>());
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), s.mult.as<double>(), O, s.max_gradient, s.scratch.as<int>(),
+      reinterpret_cast<unsigned long long*>(s.scratch.as<char>() + 8));
   s.launches += 1;
-  int flags = 0;
-  CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+  struct { int flags; int pad; unsigned long long n0, n1, nm1; } vh;
+  CK(cudaMemcpyAsync(&vh, s.scratch.p, sizeof vh, cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
+  const int flags = vh.flags;
   s.has_nonfinite = (flags & 2) != 0;
   if (flags & 1)
     return fail(errp, ADEPT_CUDA_ERR_RANGE,
                 "malformed tape: a slot index is outside [0,max_gradient) or statement ends are not monotone");
+  // Stack::fraction_multipliers_equal_to (include/adept/Stack.h:707-715) for 0, +1, -1, of the tape as recorded
+  s.stat["frac_mult_zero"] = O > 0 ? double(vh.n0) / double(O) : 0.0;
+  s.stat["frac_mult_one"] = O > 0 ? double(vh.n1) / double(O) : 0.0;
+  s.stat["frac_mult_minus_one"] = O > 0 ? double(vh.nm1) / double(O) : 0.0;
+  s.stat["ops_removed"] = 0.0;
+  s.stat["n_ops_recorded"] = double(O);
+  // 1b. tape compaction (option "remove_null"): drop the zero-multiplier operations, as a reference built with
+  //     -DADEPT_REMOVE_NULL_STATEMENTS would have done while recording; everything below sees the compacted tape
+  if (c->opt_remove_null && vh.n0 > 0) {
+    s.pool.resize(kPoolSlots);
+    Buf &keep = s.pool[41], &pos = s.pool[42], &tmpc = s.pool[9], &m2 = s.pool[43], &i2 = s.pool[44];
+    const int64_t O2 = O - int64_t(vh.n0);
+    RET(ensure(errp, keep, size_t(O + 1) * 4));
+    RET(ensure(errp, pos, size_t(O + 1) * 4));
+    RET(ensure(errp, m2, size_t(std::max<int64_t>(O2, 1)) * 8));
+    RET(ensure(errp, i2, size_t(std::max<int64_t>(O2, 1)) * 4));
+    CK(cudaMemsetAsync(keep.as<int32_t>() + O, 0, 4, s.stream));
+    compact_keep_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(s.mult.as<double>(), O, keep.as<int32_t>());
+    RET(exclusive_sum(errp, s, tmpc, keep.as<int32_t>(), pos.as<int32_t>(), O + 1));
+    compact_ops_kernel<<<grid_for(O, T, s.sm_count), T, 0, s.stream>>>(s.mult.as<double>(), s.idx.as<int32_t>(), O, keep.as<int32_t>(),
+                                                                      pos.as<int32_t>(), m2.as<double>(), i2.as<int32_t>());
+    compact_stmt_kernel<<<grid_for(s.n_stmt, T, s.sm_count), T, 0, s.stream>>>(s.stmt.as<int2>(), s.n_stmt, pos.as<int32_t>());
+    s.launches += 3;
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    std::swap(s.mult, m2);     // the recorded arrays go back to the pool
+    std::swap(s.idx, i2);
+    s.n_ops = O2;
+    const double f0 = s.stat["frac_mult_zero"], f1 = s.stat["frac_mult_one"], fm1 = s.stat["frac_mult_minus_one"];
+    const int rc = build_schedule(c, s);   // once more on the compacted tape (no zero multipliers left: one level deep)
+    s.stat["frac_mult_zero"] = f0;         // the statistics describe the tape as recorded
+    s.stat["frac_mult_one"] = f1;
+    s.stat["frac_mult_minus_one"] = fm1;
+    s.stat["ops_removed"] = double(vh.n0);
+    s.stat["n_ops_recorded"] = double(O);
+    return rc;
+  }
   s.stat["an_validate_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count();
   tp = std::chrono::steady_clock::now();
   // 2. tape-order streams
@@ -736,7 +777,8 @@ void publish_schedule_stats(adept_cuda_ctx* c) {
   c->stat["n_records"] = double(s.R);
   c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
   c->stat["kernel_launches"] = c->total_launches();
-  for (const char* k : {"analysis_ms", "an_validate_ms", "an_window_ms", "an_pack_ms", "an_forward_ms", "an_target_ms", "an_fused_ms"}) {
+  for (const char* k : {"analysis_ms", "an_validate_ms", "an_window_ms", "an_pack_ms", "an_forward_ms", "an_target_ms", "an_fused_ms",
+                        "frac_mult_zero", "frac_mult_one", "frac_mult_minus_one", "ops_removed", "n_ops_recorded"}) {
     auto it = s.stat.find(k);
     if (it != s.stat.end()) c->stat[k] = it->second;
   }
@@ -2202,6 +2244,7 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   CK(cudaStreamSynchronize(s.stream));
   s.n_stmt = n_stmt;
   s.n_ops = n_ops;
+  s.n_ops_recorded = n_ops;
   s.max_gradient = max_gradient;
   s.have_tape = true;
   c->epoch = epoch;
@@ -2298,7 +2341,7 @@ int adept_cuda_tape_epoch(const adept_cuda_ctx* c, uint64_t* epoch, int64_t* n_s
   if (!c->sh[0].have_tape) return ADEPT_CUDA_ERR_NO_TAPE;
   if (epoch) *epoch = c->epoch;
   if (n_stmt) *n_stmt = c->sh[0].n_stmt;
-  if (n_ops) *n_ops = c->sh[0].n_ops;
+  if (n_ops) *n_ops = c->sh[0].n_ops_recorded;
   return 0;
 }
 
@@ -2610,6 +2653,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "remove_null") {
+    c->opt_remove_null = value ? 1 : 0;
   } else if (k == "profile_every") {
     if (value < 0) return fail(errp, ADEPT_CUDA_ERR_ARG, "profile_every must be >= 0");
     c->opt_profile_every = int(value);

@@ -30,15 +30,35 @@ __device__ __forceinline__ int64_t stmt_of_op(const int2* __restrict__ stmt, int
 }
 
 // flags[0] |= 1 on any malformed entry (slot out of range, ends not monotone), |= 2 on a non-finite multiplier.
+// counts[0..2] += number of multipliers equal to 0, +1, -1 (Stack::fraction_multipliers_equal_to,
+// include/adept/Stack.h:707-715); counts may be null.
 __global__ void validate_kernel(const int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ idx,
-                                const double* __restrict__ mult, int64_t n_ops, int64_t max_gradient, int* flags) {
+                                const double* __restrict__ mult, int64_t n_ops, int64_t max_gradient, int* flags,
+                                unsigned long long* counts = nullptr) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   bool bad = false, nonfinite = false;
+  unsigned int n0 = 0, n1 = 0, nm1 = 0;
   for (int64_t o = t; o < n_ops; o += stride) {
     const int32_t x = idx[o];
     if (x < 0 || x >= max_gradient) bad = true;
-    if (mult && !isfinite(mult[o])) nonfinite = true;
+    if (mult) {
+      const double m = mult[o];
+      if (!isfinite(m)) nonfinite = true;
+      n0 += (m == 0.0);
+      n1 += (m == 1.0);
+      nm1 += (m == -1.0);
+    }
+  }
+  if (counts) {
+    n0 = __reduce_add_sync(0xffffffffu, n0);
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    nm1 = __reduce_add_sync(0xffffffffu, nm1);
+    if ((threadIdx.x & 31) == 0) {
+      if (n0) atomicAdd(&counts[0], static_cast<unsigned long long>(n0));
+      if (n1) atomicAdd(&counts[1], static_cast<unsigned long long>(n1));
+      if (nm1) atomicAdd(&counts[2], static_cast<unsigned long long>(nm1));
+    }
   }
   for (int64_t s = t; s < n_stmt; s += stride) {
     const int2 st = stmt[s];
@@ -52,6 +72,36 @@ __global__ void validate_kernel(const int2* __restrict__ stmt, int64_t n_stmt, c
   }
   if (bad) atomicOr(flags, 1);
   if (nonfinite) atomicOr(flags, 2);  // 0*inf must stay NaN: forward sweeps then evaluate every statement
+}
+
+// ---------------------------------------------------------------------------------------
+// Tape compaction on upload (option "remove_null"): operations whose multiplier is zero are dropped, exactly what
+// the reference does AT RECORDING TIME when built with -DADEPT_REMOVE_NULL_STATEMENTS
+// (include/adept/StackStorageOrig.h:46-65: push_rhs stores the pair only `if (multiplier != 0.0)`).  Statements keep
+// their place (a statement left without operations still overwrites its LHS with zero).  keep[o] = 1 for the
+// operations that stay; pos = exclusive scan of keep.
+// ---------------------------------------------------------------------------------------
+__global__ void compact_keep_kernel(const double* __restrict__ mult, int64_t n_ops, int32_t* __restrict__ keep) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = t; o < n_ops; o += stride) keep[o] = (mult[o] != 0.0) ? 1 : 0;   // NaN != 0: kept, like the reference
+}
+__global__ void compact_ops_kernel(const double* __restrict__ mult, const int32_t* __restrict__ idx, int64_t n_ops,
+                                   const int32_t* __restrict__ keep, const int32_t* __restrict__ pos,
+                                   double* __restrict__ mult_out, int32_t* __restrict__ idx_out) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = t; o < n_ops; o += stride)
+    if (keep[o]) {
+      mult_out[pos[o]] = mult[o];
+      idx_out[pos[o]] = idx[o];
+    }
+}
+// new end of every statement = number of kept operations before its old end (pos has n_ops + 1 entries)
+__global__ void compact_stmt_kernel(int2* __restrict__ stmt, int64_t n_stmt, const int32_t* __restrict__ pos) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t s = t; s < n_stmt; s += stride) stmt[s].y = pos[stmt[s].y];
 }
 
 // Tape-order streams.  One thread per record of the forward stream.

@@ -182,6 +182,12 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
                      between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
+     "remove_null"   1 = tape compaction on upload: operations whose multiplier is zero are dropped, as a reference built
+                     with -DADEPT_REMOVE_NULL_STATEMENTS does while recording (include/adept/StackStorageOrig.h:46-65);
+                     results then equal THAT build's bit for bit (and the default build's whenever no gradient is inf/NaN:
+                     0*inf is the only thing a dropped term could have contributed).  Default 0.  Takes effect at the next
+                     upload.  Stats: "ops_removed", and for every tape "frac_mult_zero" / "frac_mult_one" /
+                     "frac_mult_minus_one" (Stack::fraction_multipliers_equal_to, include/adept/Stack.h:707-715)
      "profile_every" N > 0: cudaProfilerStart/Stop around every N-th launch of a level sweep (for
                      `ncu --profile-from-start off`); the bracketed launches are listed in $ADEPT_CUDA_PROFILE_LOG
 */

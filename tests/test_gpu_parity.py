@@ -445,3 +445,51 @@ def test_device_resident_sweeps(engine, po, pkg):
         engine.tangent_linear_device(d.data_ptr(), flags)      # twice on the same vector, as test_derivatives.cpp:25-29 does
         want = po.tangent_linear(t["stmt"], t["mult"], t["idx"], po.tangent_linear(t["stmt"], t["mult"], t["idx"], x))
         assert same_bits(d.cpu().numpy(), want)
+
+
+# ---- tape compaction on upload -----------------------------------------------------------------
+def prune_null(t):
+    """What a reference built with -DADEPT_REMOVE_NULL_STATEMENTS records (include/adept/StackStorageOrig.h:46-65):
+    push_rhs drops a pair whose multiplier is zero; statements stay."""
+    keep = t["mult"] != 0.0
+    pos = np.concatenate([[0], np.cumsum(keep)])
+    stmt = t["stmt"].copy()
+    stmt[:, 1] = pos[stmt[:, 1]]
+    return dict(t, stmt=stmt.astype(np.int32), mult=np.ascontiguousarray(t["mult"][keep]), idx=np.ascontiguousarray(t["idx"][keep]))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_remove_null_matches_the_reference_built_with_remove_null_statements(engine, po, pkg, seed):
+    rng = np.random.default_rng(40 + seed)
+    t = pkg.tapegen.random_small_tape(rng, 4000 + 900 * seed, 150, n_indep=9, n_dep=7, lhs_any_prob=0.1)
+    m = t["mult"]
+    m[rng.random(m.size) < 0.25] = 0.0
+    m[rng.random(m.size) < 0.05] = -0.0
+    m[rng.random(m.size) < 0.1] = 1.0
+    m[rng.random(m.size) < 0.1] = -1.0
+    if seed == 2:                         # 0 * inf: the one thing a dropped term could have contributed
+        m[rng.integers(0, m.size, 8)] = np.inf
+    p = prune_null(t)
+    assert p["idx"].size < t["idx"].size
+    try:
+        for schedule, window in ((LEVELS, 0), (LEVELS, 97), (UNFUSED, 97), (SMALLG, 0), (ORDERED, 0)):
+            engine.set_option("remove_null", 1)
+            upload(engine, t, schedule, window)
+            assert engine.stat("ops_removed") == t["idx"].size - p["idx"].size
+            assert engine.stat("frac_mult_zero") == np.mean(m == 0.0)                 # Stack::fraction_multipliers_equal_to
+            assert engine.stat("frac_mult_one") == np.mean(m == 1.0) and engine.stat("frac_mult_minus_one") == np.mean(m == -1.0)
+            for mode in (0, 1):
+                got = engine.jacobian(mode, t["indep"], t["dep"])
+                rc, want = po.jacobian(p["stmt"], p["mult"], p["idx"], p["max_gradient"], p["indep"], p["dep"], mode)
+                assert rc == 0 and same_bits(got, want), (schedule, window, mode)
+            g0 = rng.uniform(-1, 1, t["max_gradient"])
+            flags = pkg.SWEEP_ORDERED if schedule == ORDERED else 0
+            assert same_bits(engine.adjoint(g0, True, flags), po.adjoint(p["stmt"], p["mult"], p["idx"], g0))
+            assert same_bits(engine.tangent_linear(g0, True, flags), po.tangent_linear(p["stmt"], p["mult"], p["idx"], g0))
+            # the default (no compaction) keeps every recorded term
+            engine.set_option("remove_null", 0)
+            upload(engine, t, schedule, window)
+            assert engine.stat("ops_removed") == 0
+            check_jacobians(engine, po, t, "recorded tape")
+    finally:
+        engine.set_option("remove_null", 0)
