@@ -101,6 +101,7 @@ struct Shard {
   std::vector<int64_t> step_group;    // [n_levels+2] first target group of each step
   std::vector<int64_t> step_tchunk;   // [n_levels+2] first target chunk of each step
   std::vector<int64_t> step_recs;       // [n_levels+2] forward records (operations + statements) of each step
+  std::vector<uint8_t> level_long;      // [n_levels+2] the step holds a chunk that may exceed one staged piece
   std::vector<std::string> prof_log;    // option "profile_every": one line per launch handed to the profiler
   std::vector<LongStmt> long_stmts;     // sorted by schedule position (hence by step)
   Buf long_tab;                         // device copy: {b, e} record range of every long statement, same order
@@ -183,6 +184,8 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_wide_streams = 0;   // > 0: this many streams for the forward level sweep even when its steps are wide (experiments)
+  int opt_fwd_balanced = 1;   // forward level sweep: balanced CTA shape (forward_balanced_kernel); 0: forward_level_kernel only
   int opt_remove_null = 0;    // 1: drop zero-multiplier operations on upload (the reference's ADEPT_REMOVE_NULL_STATEMENTS build)
   int opt_profile_every = 0;  // > 0: cudaProfilerStart/Stop around every Nth launch of a level sweep (ncu --profile-from-start off)
   // stats
@@ -659,6 +662,16 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   chunk_flags_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), k0.as<uint32_t>(), S,
                                                                      chunk_recs, flag.as<int32_t>());
   s.launches += 1;
+  {  // steps whose chunks may be longer than one staged piece go to the streaming forward kernel
+    Buf& ll = s.pool[45];
+    RET(ensure(errp, ll, size_t(n_levels) + 2));
+    CK(cudaMemsetAsync(ll.p, 0, size_t(n_levels) + 2, s.stream));
+    mark_long_levels_kernel<<<grid_for(S, T, s.sm_count), T, 0, s.stream>>>(s.foff.as<int64_t>(), k0.as<uint32_t>(), S,
+                                                                            int64_t(kPieceRecs) - chunk_recs, ll.as<uint8_t>());
+    s.launches += 1;
+    s.level_long.assign(size_t(n_levels) + 2, 0);
+    CK(cudaMemcpyAsync(s.level_long.data(), ll.p, size_t(n_levels) + 2, cudaMemcpyDeviceToHost, s.stream));
+  }
   RET(exclusive_sum(errp, s, tmp, flag.as<int32_t>(), cid.as<int32_t>(), S + 1));
   int32_t n_chunks32 = 0;
   CK(cudaMemcpyAsync(&n_chunks32, cid.as<int32_t>() + S, 4, cudaMemcpyDeviceToHost, s.stream));
@@ -1110,12 +1123,26 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     if (F.n_colblocks >= 16 && F.n_colblocks / fwarps < c->opt_streams)
       fwarps = std::max(1, std::min(fwarps, F.n_colblocks / std::max(1, c->opt_streams)));
     const bool sparse = !s.has_nonfinite;
+    const bool balanced = c->opt_fwd_balanced != 0;
+    // balanced kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
+    // groups are kept for the streams below
+    int cbs = kFwdCbs;
+    if (c->opt_cbs > 0) cbs = int(std::min<int64_t>(c->opt_cbs, kFwdCbs));
+    else if (F.n_colblocks < kFwdCbs * c->opt_streams)
+      cbs = std::max(std::min(8, F.n_colblocks), (F.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
+    cbs = std::max(1, std::min(cbs, kFwdCbs));
+    F.cbs = cbs;
+    const int bwarps = std::max(1, std::min(plan.warps, cbs));
     // independent direction ranges on separate streams, one issuing host thread each (see the reverse sweep)
     const int all_cb = F.n_colblocks;
-    const int groups = (all_cb + fwarps - 1) / fwarps;
+    const int gwidth = balanced ? cbs : fwarps;   // column blocks per stream-partition unit
+    const int groups = (all_cb + gwidth - 1) / gwidth;
     int nstr = std::max(1, std::min<int>(c->opt_streams, groups));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= kWideStepCtas || c->opt_time_kernels || c->opt_profile_every) nstr = 1;
+    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= (balanced ? kWideStepCtas / 4 : kWideStepCtas) ||
+        c->opt_time_kernels || c->opt_profile_every)
+      nstr = 1;
+    if (c->opt_wide_streams > 0) nstr = std::max(1, std::min<int>(c->opt_wide_streams, groups));
     s.stat["sweep_streams"] = nstr;
     while (int(s.aux.size()) < nstr - 1) {
       cudaStream_t st;
@@ -1138,13 +1165,16 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       if (g_hi <= g_lo) return;
       cudaStream_t st = (i == 0) ? s.stream : s.aux[i - 1];
       ForwardArgs Fi = F;
-      Fi.cb_lo = g_lo * fwarps;
-      Fi.n_colblocks = std::min(all_cb, g_hi * fwarps);
+      Fi.cb_lo = g_lo * gwidth;
+      Fi.n_colblocks = std::min(all_cb, g_hi * gwidth);
+      const int ncols = Fi.n_colblocks - Fi.cb_lo;
       for (int32_t l = 1; l <= s.n_levels; ++l) {
         const int64_t c0 = s.level_chunk[l], c1 = s.level_chunk[l + 1];
         if (c1 <= c0) continue;
         Fi.first_chunk = c0;
-        const dim3 grid(unsigned(c1 - c0), unsigned(g_hi - g_lo));
+        const bool use_bal = balanced && !s.level_long[l];
+        const dim3 grid(unsigned(c1 - c0), unsigned(use_bal ? (ncols + cbs - 1) / cbs : (ncols + fwarps - 1) / fwarps));
+        const dim3 block(unsigned((use_bal ? bwarps : fwarps) * 32));
         if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         const bool prof = c->opt_profile_every > 0 && (int64_t(nl[i]) % c->opt_profile_every) == 0;
         if (prof) {
@@ -1152,8 +1182,13 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
             cudaProfilerStart();
         }
         cudaError_t le;
-        if (sparse) le = launch_pdl(forward_level_kernel<V, true>, grid, dim3(fwarps * 32), st, pdl && !prof, Fi);
-        else le = launch_pdl(forward_level_kernel<V, false>, grid, dim3(fwarps * 32), st, pdl && !prof, Fi);
+        if (use_bal) {
+          if (sparse) le = launch_pdl(forward_balanced_kernel<V, true>, grid, block, st, pdl && !prof, Fi);
+          else le = launch_pdl(forward_balanced_kernel<V, false>, grid, block, st, pdl && !prof, Fi);
+        } else {
+          if (sparse) le = launch_pdl(forward_level_kernel<V, true>, grid, block, st, pdl && !prof, Fi);
+          else le = launch_pdl(forward_level_kernel<V, false>, grid, block, st, pdl && !prof, Fi);
+        }
         if (le != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         if (prof) {
           cudaStreamSynchronize(st);
@@ -2653,6 +2688,11 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "wide_streams") {
+    if (value < 0 || value > 8) return fail(errp, ADEPT_CUDA_ERR_ARG, "wide_streams must be in 0..8");
+    c->opt_wide_streams = int(value);
+  } else if (k == "fwd_balanced") {
+    c->opt_fwd_balanced = value ? 1 : 0;
   } else if (k == "remove_null") {
     c->opt_remove_null = value ? 1 : 0;
   } else if (k == "profile_every") {

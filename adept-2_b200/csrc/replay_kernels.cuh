@@ -943,6 +943,7 @@ struct ForwardArgs {
   int n_colblocks;   // column blocks [cb_lo, n_colblocks) are handled by this launch
   int cb_lo;
   int flag_pitch;
+  int cbs;           // forward_balanced_kernel: column blocks per CTA (<= kFwdCbs)
 };
 
 template <int V, bool SPARSE>
@@ -1040,6 +1041,169 @@ __global__ void __launch_bounds__(256, 3) forward_level_kernel(ForwardArgs A) {
     }
     __syncthreads();
     if (threadIdx.x == 0 && p + kStages < n_pieces) issue_piece(ring, chunk, n_recs, p + kStages);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Level-scheduled forward sweep, balanced form (round 2).  Same stream, same arithmetic, same bits as
+// forward_level_kernel above; different CTA shape.  ncu on the kernel above (BASELINE config 4, wide step): 27 warp
+// instructions per (record, column block) -- every warp re-reads and re-decodes every record -- and issue slots 57 %
+// busy on a kernel that should only wait for HBM.  Here, as in reverse_fused_kernel:
+//   * a CTA owns one chunk (one staged piece of <= 256 records) and up to 32 column blocks (A.cbs); the activity
+//     bytes of all its (record, column block) pairs are fetched in ONE round trip, and the warps take the column
+//     blocks that have anything to do in turn;
+//   * per block of 32 records the lanes decode ONE record each (row byte offset, flags, multiplier) and park the
+//     statement ends and the ACTIVE operations, compacted and in order, in the warp's shared-memory list; the
+//     serial walk then costs a 16-byte shared-memory read and a 64-bit add per record, eight 16-byte row loads in
+//     flight per lane.
+// Chunks longer than one piece (a statement of more than ~128 operands) are left to the kernel above: the host
+// picks the kernel per step (Shard::level_long).
+// ---------------------------------------------------------------------------------------
+constexpr int kFwdCbs = 32;
+
+template <int V, bool SPARSE>
+__device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
+                                             const uint32_t* __restrict__ tailm, uint4* __restrict__ wl,
+                                             double* __restrict__ gcol, uint8_t* __restrict__ ract, int64_t K, int ncb,
+                                             int lane) {
+  // list entry: x = low word of the row's byte offset | 1 (statement end) | 2 (load the row) | 4 (statement end whose
+  // row currently holds data), y = high word, (z, w) = multiplier bits (operation) or z = row (statement end)
+  LaneVec<V> acc;
+  acc.zero();
+  bool open_active = false;   // the statement being summed has had an active operand
+  char* const gbase = reinterpret_cast<char*>(gcol);
+  const uint32_t Kb = static_cast<uint32_t>(K) * 8u;   // bytes per row: a multiple of 512, the low bits are free
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int nblk = (n + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int i = (blk << 5) + lane;
+    const bool valid = i < n;
+    const uint32_t tm = tailm[blk];
+    const bool is_tail = (tm >> lane) & 1u;
+    const uint8_t pfb = (SPARSE && valid) ? pfw[i] : 0;
+    const bool a = valid && !is_tail && (!SPARSE || pfb != 0);
+    const uint32_t act = __ballot_sync(0xffffffffu, a);
+    const uint32_t work = act | tm;
+    if (work == 0u) continue;
+    if ((work >> lane) & 1u) {
+      const Rec rc = r[i];
+      const uint64_t off = static_cast<uint64_t>(static_cast<uint32_t>(rc.slot)) * Kb;
+      uint4 e;
+      e.x = static_cast<uint32_t>(off) | (is_tail ? 1u : 0u) | (a ? 2u : 0u) | ((is_tail && pfb) ? 4u : 0u);
+      e.y = static_cast<uint32_t>(off >> 32);
+      const uint64_t mb = static_cast<uint64_t>(__double_as_longlong(rc.m));
+      e.z = is_tail ? static_cast<uint32_t>(rc.slot) : static_cast<uint32_t>(mb);
+      e.w = static_cast<uint32_t>(mb >> 32);
+      wl[__popc(work & lt_mask)] = e;
+    }
+    __syncwarp();
+    const int cnt = __popc(work);
+    for (int j = 0; j < cnt; j += kBatch) {
+      LaneVec<V> v[kBatch];
+      // all loads of a step are independent of its stores (RAW/WAR between the statements of a step are excluded
+      // by the schedule; a statement's own operands precede its end)
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        v[u].zero();
+        if (j + u < cnt) {
+          const uint2 e = *reinterpret_cast<const uint2*>(&wl[j + u]);
+          if (e.x & 2u)
+            v[u].load(reinterpret_cast<const double*>(gbase + ((static_cast<uint64_t>(e.y) << 32) | (e.x & ~15u))));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (j + u >= cnt) break;
+        const uint4 e = wl[j + u];
+        if (e.x & 1u) {   // the statement is complete
+          double* dst = reinterpret_cast<double*>(gbase + ((static_cast<uint64_t>(e.y) << 32) | (e.x & ~15u)));
+          if (!SPARSE || open_active) {
+            acc.store(dst);
+            if (SPARSE && lane == 0) ract[static_cast<int64_t>(e.z) * ncb] = 1;
+          } else if (e.x & 4u) {   // the result is +0.0 but the row still holds an older value
+            acc.store(dst);        // acc is +0.0 here
+            if (lane == 0) ract[static_cast<int64_t>(e.z) * ncb] = 0;
+          }
+          acc.zero();
+          open_active = false;
+        } else {
+          const double m = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(e.w) << 32) | e.z));
+          acc.x = mul_add_rn(acc.x, m, v[u].x);
+          if (V == 2) {
+            double* cv = reinterpret_cast<double*>(&acc);
+            cv[V - 1] = mul_add_rn(cv[V - 1], m, reinterpret_cast<const double*>(&v[u])[V - 1]);
+          }
+          open_active = true;
+        }
+      }
+    }
+    __syncwarp();   // the list is rewritten for the next block
+  }
+}
+
+template <int V, bool SPARSE>
+__global__ void __launch_bounds__(256, 4) forward_balanced_kernel(ForwardArgs A) {
+  __shared__ __align__(16) Rec recs[kPieceRecs];
+  __shared__ __align__(8) uint64_t full;
+  __shared__ __align__(4) uint8_t pf[kFwdCbs * kPfPitch];   // pf[w*kPfPitch + i]: record i, column block cb0 + w
+  __shared__ uint32_t tailm[kPieceRecs / 32];
+  __shared__ uint4 wlist[8][32];
+  __shared__ uint32_t smask;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int ncb = A.flag_pitch;
+  const int64_t c = A.first_chunk + blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&full, 1);
+    mbar_fence_init();
+    smask = 0u;
+  }
+  __syncthreads();
+  pdl_trigger();
+  const int64_t r0 = A.chunk_begin[c], r1 = A.chunk_begin[c + 1];
+  const int n = static_cast<int>(r1 - r0);   // <= kPieceRecs: the host sends longer chunks to forward_level_kernel
+  const int cb0 = A.cb_lo + blockIdx.y * A.cbs;
+  const int cbs = min(A.cbs, A.n_colblocks - cb0);
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(n) * static_cast<uint32_t>(sizeof(Rec));
+    mbar_expect_tx(&full, bytes);
+    tma_bulk_g2s(&recs[0], A.recs + r0, bytes, &full);
+  }
+  pdl_wait();   // records (immutable) are already in flight; gradient rows and activity bytes come from the previous step
+  mbar_wait(&full, 0u);
+  const Rec* r = &recs[0];
+  // statement-end mask of every block of 32 records
+  for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
+    const int32_t kind = i < n ? r[i].kind : REC_OP;
+    const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
+    if (lane == 0) tailm[i >> 5] = h;
+  }
+  uint32_t mask;
+  if (SPARSE) {
+    // activity bytes: thread t -> record t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
+    uint32_t seen = 0u;   // column blocks in which this thread saw an active operand or a live result row
+    for (int t = threadIdx.x; t < n * cbs; t += blockDim.x) {
+      const int i = t / cbs, w = t - i * cbs;
+      const uint8_t f = A.rowact[static_cast<int64_t>(r[i].slot) * ncb + cb0 + w];
+      pf[w * kPfPitch + i] = f;
+      if (f) seen |= 1u << w;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
+    if (lane == 0 && seen) atomicOr(&smask, seen);
+    __syncthreads();
+    mask = smask;
+  } else {
+    __syncthreads();
+    mask = cbs >= 32 ? 0xffffffffu : ((1u << cbs) - 1u);
+  }
+  int k = 0;
+  for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
+    if (k % nwarps != warp) continue;
+    const int w = __ffs(mm) - 1;
+    const int cb = cb0 + w;
+    forward_task<V, SPARSE>(r, n, &pf[w * kPfPitch], tailm, &wlist[warp][0],
+                            A.g + (static_cast<int64_t>(cb) * 32 + lane) * V, A.rowact + cb, A.K, ncb, lane);
   }
 }
 

@@ -638,6 +638,15 @@ __global__ void chunk_flags_kernel(const int64_t* __restrict__ foff, const uint3
   }
 }
 
+// steps that hold a statement of more than `thresh` records (its chunk may exceed one staged piece): flag[step] = 1
+__global__ void mark_long_levels_kernel(const int64_t* __restrict__ foff, const uint32_t* __restrict__ sched_level, int64_t S,
+                                        int64_t thresh, uint8_t* __restrict__ flag) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j = t; j < S; j += stride)
+    if (foff[j + 1] - foff[j] > thresh) flag[sched_level[j]] = 1;
+}
+
 // chunk tables: fwd_chunk[c] = foff[j] for the c-th flagged j; fwd_chunk[n_chunks] = R;
 // rev_chunk[c'] = R - fwd_chunk[n_chunks - c']; level_chunk[l] = chunk id of level_first[l].
 __global__ void chunk_tables_kernel(const int64_t* __restrict__ foff, const int32_t* __restrict__ flag,

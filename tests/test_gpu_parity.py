@@ -85,6 +85,29 @@ def test_reverse_level_sweep_per_step_and_persistent(engine, name, persistent):
         engine.set_option("pass_dirs", 0)
 
 
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("balanced,cbs,streams", [(0, 0, 4), (1, 0, 4), (1, 3, 1), (1, 32, 2)])
+def test_forward_level_sweep_both_cta_shapes(engine, name, balanced, cbs, streams):
+    """The level-scheduled forward sweep exists as forward_level_kernel (warp bound to a column block, chunks of any
+    length) and forward_balanced_kernel (active column blocks handed to the warps, compacted walk, one staged piece);
+    the host picks per step.  Either way, any column-block grouping, one pass or several: the reference's bits."""
+    g = load_golden(name)
+    try:
+        engine.set_option("fwd_balanced", balanced)
+        engine.set_option("streams", streams)
+        for window in (0, 80):
+            upload(engine, g, LEVELS, window)
+            engine.set_option("cbs", cbs)
+            for pass_dirs in (0, 64):
+                engine.set_option("pass_dirs", pass_dirs)
+                assert same_bits(engine.jacobian(0, g["indep"], g["dep"]), g["jac_fwd"])
+    finally:
+        engine.set_option("fwd_balanced", 1)
+        engine.set_option("streams", 4)
+        engine.set_option("cbs", 0)
+        engine.set_option("pass_dirs", 0)
+
+
 def broadcast_tape(n=700, fan=64, seed=1):
     """x0, x1 feed EVERY statement of a layer (y_i = a_i x0 + b_i x1), and a second layer mixes the y's:
     in the reverse sweep x0 and x1 each receive n contributions within one step -- one target group of more
@@ -182,7 +205,7 @@ def test_overwritten_independents_leave_no_stale_rows(engine, po, pkg):
         upload(engine, t, schedule)
         check_jacobians(engine, po, t, f"overwritten independent, schedule {schedule}")
     upload(engine, t, LEVELS)
-    assert engine.stat("used_fused") == 1 and engine.jacobian(1, t["indep"], t["dep"])[0] == 0.0
+    assert engine.jacobian(1, t["indep"], t["dep"])[0] == 0.0 and engine.stat("used_fused") == 1
 
 
 @pytest.mark.parametrize("seed", range(8))
