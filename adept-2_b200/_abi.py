@@ -38,6 +38,8 @@ SIGNATURES = {
     "adept_cuda_adjoint_device": (C.c_int, [_vp, _vp, C.c_int]),
     "adept_cuda_jacobian_batch": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _i64, _vp, _i64,
                                             _vp, _i64, _vp, _i64, _vp]),
+    "adept_cuda_host_alloc": (_vp, [C.c_size_t]),
+    "adept_cuda_host_free": (None, [_vp]),
     "adept_cuda_chain_begin": (C.c_int, [_vp, _i64, _vp]),
     "adept_cuda_chain_push": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64]),
     "adept_cuda_chain_end": (C.c_int, [_vp, _vp]),

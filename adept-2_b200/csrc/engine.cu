@@ -107,6 +107,10 @@ struct Shard {
   Buf long_tab;                         // device copy: {b, e} record range of every long statement, same order
   // workspace
   Buf g, abuf, rowact, aflag, seed_slots, out_slots, out, g1, a1, scratch, agree_buf;
+  // ensemble pipeline (adept_cuda_jacobian_batch): two buffer sets, copy-in and copy-out streams
+  Buf bg[2], bmult[2], bout[2];
+  cudaStream_t bcopy = nullptr, bback = nullptr;
+  cudaEvent_t b_in[2] = {nullptr, nullptr}, b_done[2] = {nullptr, nullptr}, b_out[2] = {nullptr, nullptr};
   // optional per-launch timing of the dominant replay kernel (option "time_kernels")
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
@@ -184,6 +188,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_batch_chunks = 4;   // ensemble entry point: chunks per device through the copy-in / sweep / copy-out pipeline
   int opt_wide_streams = 0;   // > 0: this many streams for the forward level sweep even when its steps are wide (experiments)
   int opt_fwd_balanced = 1;   // forward level sweep: balanced CTA shape (forward_balanced_kernel); 0: forward_level_kernel only
   int opt_remove_null = 0;    // 1: drop zero-multiplier operations on upload (the reference's ADEPT_REMOVE_NULL_STATEMENTS build)
@@ -566,9 +571,11 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       int32_t* need_w = need.as<int32_t>() + h_base[w];
       int32_t* gmap_w = gmap.as<int32_t>() + h_base[w];
       const int64_t total = (o1 - o0) + (hi - lo + 1);
-      window_need_kernel<<<grid_for(total, T, s.sm_count), T, 0, s.stream>>>(
+      // ~1200 elements per CTA: few enough CTAs for few global atomics, enough of them to fill the machine
+      const int need_grid = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(s.sm_count) * 4, (total + 1023) / 1024)));
+      window_need_kernel<<<need_grid, T, 0, s.stream>>>(
           s.stmt.as<int2>(), s.idx.as<int32_t>(), lo, hi, o0, o1, s.level.as<int32_t>(), gw.as<int32_t>(), gr.as<int32_t>(),
-          need_w);
+          need_w, depth);
       window_map_kernel<<<1, 32, 0, s.stream>>>(need_w, depth, gmap_w);
       if (lo == hi) {
         window_update_single_ops_kernel<<<grid_for(std::max<int64_t>(o1 - o0, 1), T, s.sm_count), T, 0, s.stream>>>(
@@ -2002,6 +2009,14 @@ void free_shard(Shard& s) {
   }
   for (int k = 0; k < 2; ++k)
     if (s.ev[k]) cudaEventDestroy(s.ev[k]);
+  for (int q = 0; q < 2; ++q) {
+    release(s.bg[q]); release(s.bmult[q]); release(s.bout[q]);
+    if (s.b_in[q]) cudaEventDestroy(s.b_in[q]);
+    if (s.b_done[q]) cudaEventDestroy(s.b_done[q]);
+    if (s.b_out[q]) cudaEventDestroy(s.b_out[q]);
+  }
+  if (s.bcopy) cudaStreamDestroy(s.bcopy);
+  if (s.bback) cudaStreamDestroy(s.bback);
   for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
   for (cudaEvent_t e : s.pev) cudaEventDestroy(e);
   for (cudaEvent_t e : s.aux_ev) cudaEventDestroy(e);
@@ -2475,40 +2490,65 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
     RET(ensure(errp, s.out_slots, size_t(n_out) * 4));
     CK(cudaMemcpyAsync(s.seed_slots.p, seeds, size_t(D) * 4, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.out_slots.p, outs, size_t(n_out) * 4, cudaMemcpyHostToDevice, s.stream));
-    // members per pass from the workspace budget: per member max_gradient*Dp gradients + n_ops multipliers + outputs
+    // Members are processed in chunks through a two-deep pipeline: while chunk k is swept on the shard's stream, the
+    // multipliers of chunk k+1 are copied in on the copy stream and the Jacobians of chunk k-1 are copied out on the
+    // third one (two buffer sets).  With pinned caller memory (adept_cuda_host_alloc) the three overlap; pageable
+    // memory still works, the copies then stage through the driver.
+    // chunk size from the workspace budget: per member max_gradient*Dp gradients + n_ops multipliers + outputs, x2 sets
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes)
-                                                     : size_t(double(free_b + s.g.bytes + s.mult.bytes + s.out.bytes) * 0.6);
-    const size_t per_member = size_t(max_gradient) * Dp * 8 + size_t(n_ops) * 8 + size_t(n_dep) * n_indep * 8;
-    int64_t nb_pass = std::max<int64_t>(1, int64_t(budget / per_member));
-    nb_pass = std::min<int64_t>(nb_pass, b_hi - b_lo);
-    nb_pass = std::min<int64_t>(nb_pass, (int64_t(65535) * 8 * 32) / Dp);  // gridDim.y limit
-    for (int64_t b0 = b_lo; b0 < b_hi; b0 += nb_pass) {
-      const int64_t nb = std::min(nb_pass, b_hi - b0);
+    size_t held = s.mult.bytes;
+    for (int q = 0; q < 2; ++q) held += s.bg[q].bytes + s.bmult[q].bytes + s.bout[q].bytes;
+    const size_t budget = c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes) : size_t(double(free_b + held) * 0.6);
+    const size_t per_member = 2 * (size_t(max_gradient) * Dp * 8 + size_t(n_ops) * 8 + size_t(n_dep) * n_indep * 8);
+    const int64_t n_mine = b_hi - b_lo;
+    int64_t nb_chunk = std::max<int64_t>(1, int64_t(budget / per_member));
+    nb_chunk = std::min<int64_t>(nb_chunk, (int64_t(65535) * 8 * 32) / Dp);  // gridDim.y limit
+    const int64_t want_chunks = std::max<int64_t>(1, std::min<int64_t>(c->opt_batch_chunks, n_mine / 256));   // >= 256 members per chunk
+    nb_chunk = std::min<int64_t>(nb_chunk, (n_mine + want_chunks - 1) / want_chunks);
+    nb_chunk = std::max<int64_t>(nb_chunk, 1);
+    if (!s.bcopy) {
+      CK(cudaStreamCreateWithFlags(&s.bcopy, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&s.bback, cudaStreamNonBlocking));
+      for (int q = 0; q < 2; ++q) {
+        CK(cudaEventCreateWithFlags(&s.b_in[q], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.b_done[q], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.b_out[q], cudaEventDisableTiming));
+      }
+    }
+    CK(cudaStreamSynchronize(s.stream));   // structure, streams and slot lists are in place before the copy stream starts
+    int64_t ck = 0;
+    for (int64_t b0 = b_lo; b0 < b_hi; b0 += nb_chunk, ++ck) {
+      const int q = int(ck & 1);
+      const int64_t nb = std::min(nb_chunk, b_hi - b0);
       const int64_t lanes = nb * Dp;
       const int64_t K = ((lanes + 31) / 32) * 32;
-      RET(ensure(errp, s.g, size_t(max_gradient) * size_t(K) * 8));
-      RET(ensure(errp, s.mult, size_t(std::max<int64_t>(n_ops, 1)) * size_t(nb) * 8));
-      RET(ensure(errp, s.out, size_t(nb) * n_dep * n_indep * 8));
+      if (ck >= 2) {   // this buffer set was used by chunk ck-2: its sweep and its copy-out must be over
+        CK(cudaEventSynchronize(s.b_out[q]));
+      }
+      RET(ensure(errp, s.bg[q], size_t(max_gradient) * size_t(K) * 8));
+      RET(ensure(errp, s.bmult[q], size_t(std::max<int64_t>(n_ops, 1)) * size_t(nb) * 8));
+      RET(ensure(errp, s.bout[q], size_t(nb) * n_dep * n_indep * 8));
       if (n_ops > 0)
-        CK(cudaMemcpy2DAsync(s.mult.p, size_t(nb) * 8, multipliers + b0, size_t(n_members) * 8, size_t(nb) * 8,
-                             size_t(n_ops), cudaMemcpyHostToDevice, s.stream));
-      CK(cudaMemsetAsync(s.g.p, 0, size_t(max_gradient) * size_t(K) * 8, s.stream));
-      batch_seed_kernel<<<unsigned((nb * D + 255) / 256), 256, 0, s.stream>>>(s.g.as<double>(), K, s.seed_slots.as<int32_t>(),
+        CK(cudaMemcpy2DAsync(s.bmult[q].p, size_t(nb) * 8, multipliers + b0, size_t(n_members) * 8, size_t(nb) * 8,
+                             size_t(n_ops), cudaMemcpyHostToDevice, s.bcopy));
+      CK(cudaEventRecord(s.b_in[q], s.bcopy));
+      CK(cudaMemsetAsync(s.bg[q].p, 0, size_t(max_gradient) * size_t(K) * 8, s.stream));
+      batch_seed_kernel<<<unsigned((nb * D + 255) / 256), 256, 0, s.stream>>>(s.bg[q].as<double>(), K, s.seed_slots.as<int32_t>(),
                                                                             int(D), Dp, nb);
       s.launches += 1;
+      CK(cudaStreamWaitEvent(s.stream, s.b_in[q], 0));
       if (R > 0) {
         ReplayArgs A{};
         A.recs = (mode == 0 ? s.fwd_t : s.rev_t).as<Rec>();
         A.chunk_begin = s.one_chunk.as<int64_t>();
         A.first_chunk = 0;
-        A.g = s.g.as<double>();
+        A.g = s.bg[q].as<double>();
         A.K = K;
         A.n_colblocks = int(K / 32);
         A.n_dirs = lanes;
         A.ref_block = P;
-        A.bmult = s.mult.as<double>();
+        A.bmult = s.bmult[q].as<double>();
         A.n_members = nb;
         A.dirs_padded = Dp;
         const int warps = 8;
@@ -2519,19 +2559,38 @@ int adept_cuda_jacobian_batch(adept_cuda_ctx* c, int mode, const void* statement
       }
       const int64_t total = nb * n_out * D;
       batch_extract_kernel<<<unsigned((total + 255) / 256), 256, 0, s.stream>>>(
-          s.g.as<double>(), K, s.out_slots.as<int32_t>(), int(n_out), int(D), Dp, nb, mode, n_dep, n_indep,
-          s.out.as<double>());
+          s.bg[q].as<double>(), K, s.out_slots.as<int32_t>(), int(n_out), int(D), Dp, nb, mode, n_dep, n_indep,
+          s.bout[q].as<double>());
       s.launches += 1;
       CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(jac_out_host + b0 * n_dep * n_indep, s.out.p, size_t(nb) * n_dep * n_indep * 8,
-                         cudaMemcpyDeviceToHost, s.stream));
-      CK(cudaStreamSynchronize(s.stream));
+      CK(cudaEventRecord(s.b_done[q], s.stream));
+      CK(cudaStreamWaitEvent(s.bback, s.b_done[q], 0));
+      CK(cudaMemcpyAsync(jac_out_host + b0 * n_dep * n_indep, s.bout[q].p, size_t(nb) * n_dep * n_indep * 8,
+                         cudaMemcpyDeviceToHost, s.bback));
+      CK(cudaEventRecord(s.b_out[q], s.bback));
     }
+    CK(cudaStreamSynchronize(s.bback));
+    CK(cudaStreamSynchronize(s.stream));
+    s.stat["batch_chunks"] = double(ck);
     return 0;
   }));
+  c->stat["batch_chunks"] = c->sh[0].stat["batch_chunks"];
   c->stat["batch_wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   c->stat["kernel_launches"] = c->total_launches();
   return 0;
+}
+
+void* adept_cuda_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void adept_cuda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int adept_cuda_chain_begin(adept_cuda_ctx* c, int64_t n_handoff, const double* handoff_host) {
@@ -2688,6 +2747,9 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "batch_chunks") {
+    if (value < 1 || value > 64) return fail(errp, ADEPT_CUDA_ERR_ARG, "batch_chunks must be in 1..64");
+    c->opt_batch_chunks = int(value);
   } else if (k == "wide_streams") {
     if (value < 0 || value > 8) return fail(errp, ADEPT_CUDA_ERR_ARG, "wide_streams must be in 0..8");
     c->opt_wide_streams = int(value);

@@ -41,13 +41,58 @@ class ensemble_structure_mismatch : public adept::exception {
   }
 };
 
+// A host array of doubles in PAGE-LOCKED memory (adept_cuda_host_alloc) when that is available, so that the engine's
+// copy-in / sweep / copy-out pipeline really overlaps; plain heap memory otherwise.  Keeps its allocation when it
+// is re-filled with the same or a smaller size (an ensemble is typically recorded again and again).
+class HostBuffer {
+ public:
+  HostBuffer() : p_(0), n_(0), cap_(0), pinned_(false) {}
+  ~HostBuffer() { release(); }
+  HostBuffer(const HostBuffer&) = delete;
+  HostBuffer& operator=(const HostBuffer&) = delete;
+  void assign(size_t n, double value) {
+    if (n > cap_) {
+      release();
+      p_ = static_cast<double*>(adept_cuda_host_alloc(n * sizeof(double)));
+      pinned_ = p_ != 0;
+      if (!p_) p_ = new double[n > 0 ? n : 1];
+      cap_ = n;
+    }
+    n_ = n;
+    for (size_t i = 0; i < n; ++i) p_[i] = value;
+  }
+  void resize_uninitialised(size_t n) {
+    if (n > cap_) { n_ = 0; assign(n, 0.0); }
+    n_ = n;
+  }
+  double* data() { return p_; }
+  const double* data() const { return p_; }
+  size_t size() const { return n_; }
+  bool pinned() const { return pinned_; }
+  double& operator[](size_t i) { return p_[i]; }
+  const double& operator[](size_t i) const { return p_[i]; }
+
+ private:
+  void release() {
+    if (p_) {
+      if (pinned_) adept_cuda_host_free(p_);
+      else delete[] p_;
+    }
+    p_ = 0;
+    n_ = cap_ = 0;
+  }
+  double* p_;
+  size_t n_, cap_;
+  bool pinned_;
+};
+
 struct EnsembleTape {
   std::vector<int32_t> statements;   // {lhs slot, end_plus_one} pairs incl. the {-1,0} sentinel (Statement.h:24-30)
   std::vector<int32_t> index;        // operand slots
   std::vector<int32_t> indep, dep;   // slots of the independent / dependent variables
   int64_t max_gradient = 0;
   int64_t n_members = 0;
-  std::vector<double> multipliers;   // [operation][member]
+  HostBuffer multipliers;            // [operation][member], page-locked when possible
   int64_t n_statements() const { return static_cast<int64_t>(statements.size() / 2); }
   int64_t n_operations() const { return static_cast<int64_t>(index.size()); }
 };
@@ -77,7 +122,12 @@ template <class Record>
 void record_ensemble(int64_t n_members, Record&& record, EnsembleTape& out, int n_threads = 0) {
   static_assert(sizeof(adept::Real) == sizeof(double), "libadept_cuda replays double-precision tapes");
   static_assert(sizeof(adept::internal::Statement) == 2 * sizeof(int32_t), "Statement is {int index, int end_plus_one}");
-  out = EnsembleTape();
+  out.statements.clear();
+  out.index.clear();
+  out.indep.clear();
+  out.dep.clear();
+  out.max_gradient = 0;
+  out.multipliers.resize_uninitialised(0);   // keeps the (page-locked) allocation of an earlier recording
   out.n_members = n_members;
   if (n_members <= 0) return;
   // member 0 fixes the structure (recorded on the calling thread, with a stack of its own so that a stack the
@@ -99,7 +149,7 @@ void record_ensemble(int64_t n_members, Record&& record, EnsembleTape& out, int 
       out.indep.assign(s0.indep().begin(), s0.indep().end());
       out.dep.assign(s0.dep().begin(), s0.dep().end());
       out.max_gradient = s0.max_grad();
-      out.multipliers.assign(static_cast<size_t>(O) * static_cast<size_t>(n_members), 0.0);
+      out.multipliers.resize_uninitialised(static_cast<size_t>(O) * static_cast<size_t>(n_members));   // every element is written below
       for (int64_t o = 0; o < O; ++o) out.multipliers[static_cast<size_t>(o) * n_members] = s0.mults()[o];
     }
     const int64_t S = out.n_statements(), O = out.n_operations();

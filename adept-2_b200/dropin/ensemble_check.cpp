@@ -8,7 +8,8 @@
 //   (b) serially, member after member on ONE Stack, copying each tape out with no helper code,
 // and both are dumped so that the test can compare them.  The analytic Jacobian of every member is dumped too.
 // In `gpu` mode the ensemble Jacobians computed by adept_cuda_jacobian_batch (reverse AND forward sweeps) are
-// appended; `cpu` mode makes no CUDA call at all (this program links libadept_cuda only for that entry point).
+// appended; `cpu` mode runs no kernel (the helper merely asks libadept_cuda for page-locked memory and falls back to
+// the heap when there is no CUDA driver).
 //
 // The reference's own ensemble use case is test/simulate_radiances.cpp:52-146 (one call per state vector);
 // the radiance model is linear in temperature, which is why this check uses a model of its own.
@@ -87,6 +88,9 @@ class PeekStack : public adept::Stack {
 template <class T>
 static void put(FILE* f, const std::vector<T>& v) {
   if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f);
+}
+static void put(FILE* f, const adept_cuda::HostBuffer& v) {
+  if (v.size()) fwrite(v.data(), sizeof(double), v.size(), f);
 }
 
 int main(int argc, char** argv) {

@@ -21,6 +21,7 @@
 #ifndef ADEPT_CUDA_H
 #define ADEPT_CUDA_H 1
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -153,6 +154,12 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
                                const int32_t* dep, int64_t n_dep,
                                double* jac_out_host);
 
+/* Page-locked host memory for buffers handed to the entry points above (tape arrays, multiplier matrices, Jacobians):
+   copies from/to it are true DMA and overlap with kernels; NULL when the allocation fails.  Plain malloc'ed memory
+   is accepted everywhere too (it is staged). */
+void* adept_cuda_host_alloc(size_t bytes);
+void  adept_cuda_host_free(void* p);
+
 /* ---- knobs and introspection ------------------------------------------------------- */
 
 /* Options (key, value):
@@ -182,6 +189,8 @@ int  adept_cuda_jacobian_batch(adept_cuda_ctx* ctx, int mode,
                      between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
+     "batch_chunks"  adept_cuda_jacobian_batch: chunks per device through its copy-in / sweep / copy-out pipeline (1..64,
+                     default 4; a chunk holds at least 256 members)
      "remove_null"   1 = tape compaction on upload: operations whose multiplier is zero are dropped, as a reference built
                      with -DADEPT_REMOVE_NULL_STATEMENTS does while recording (include/adept/StackStorageOrig.h:46-65);
                      results then equal THAT build's bit for bit (and the default build's whenever no gradient is inf/NaN:

@@ -158,8 +158,25 @@ def _ref(variant: str = ""):
                                         C.POINTER(C.c_double)]
         L.ref_tape_sweep.argtypes = [vp, C.c_int, _f64p, C.c_int, C.POINTER(C.c_double)]
         L.ref_tape_sweep_uninitialised.argtypes = [vp, C.c_int]
+        if hasattr(L, "ref_ensemble_radiances"):
+            L.ref_ensemble_radiances.argtypes = [C.c_int64, C.c_int, _f64p, _f64p, C.c_int, C.POINTER(C.c_double)]
+            L.ref_ensemble_radiances.restype = C.c_int
         _ref_libs[variant] = L
     return _ref_libs[variant]
+
+
+def ref_ensemble_radiances(state, n_threads=0, variant=""):
+    """BASELINE config 3, CPU arm: the reference's own simulate_radiances() (record + Stack::jacobian per member) under
+    OpenMP, one Stack per call.  state: [members, n+1].  Returns (jacobians [members, n+1, 2], seconds)."""
+    L = _ref(variant)
+    state = _c(state, np.float64)
+    B, n1 = state.shape
+    out = np.full((B, n1, 2), np.nan)
+    sec = C.c_double()
+    rc = L.ref_ensemble_radiances(B, n1 - 1, state.reshape(-1), out.reshape(-1), int(n_threads), C.byref(sec))
+    if rc:
+        raise RuntimeError("ref_ensemble_radiances failed")
+    return out, sec.value
 
 
 class RefError(RuntimeError):

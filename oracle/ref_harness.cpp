@@ -42,6 +42,9 @@ using adept::uIndex;
 extern "C" int ref_adv_record_nx100 (int scheme, int nt, double c, const double* q0, std::vector<uIndex>* indep, std::vector<uIndex>* dep);
 extern "C" int ref_adv_record_nx128 (int scheme, int nt, double c, const double* q0, std::vector<uIndex>* indep, std::vector<uIndex>* dep);
 extern "C" int ref_adv_record_nx4096(int scheme, int nt, double c, const double* q0, std::vector<uIndex>* indep, std::vector<uIndex>* dep);
+// test/simulate_radiances.cpp, compiled unmodified into the harness (C++ linkage)
+void simulate_radiances(int n, Real surface_temperature, const Real* temperature, Real radiance[2],
+                        Real dradiance_dsurface_temperature[2], Real* dradiance_dtemperature);
 
 // test/algorithm.cpp, compiled unmodified into the harness
 adouble algorithm(const adouble x[2]);
@@ -232,6 +235,39 @@ int ref_tape_record_radiances(ref_tape* t, int n, double surface_temperature,
     for (size_t i = 0; i < dep.size(); ++i)   { SlotRef r = {dep[i]};   s.dependent(r); }
     return 0;
   } catch (const std::exception& e) { t->err = e.what(); return 1; }
+}
+
+/* BASELINE config 3, CPU arm: the reference's OWN simulate_radiances() (test/simulate_radiances.cpp:52-146, compiled
+   unmodified into this library) for every member of an ensemble, under OpenMP with one Stack per call -- the
+   function makes its own adept::Stack, thread-local by the reference's design (include/adept/Stack.h:52-61).
+   state: [member][n+1] = surface temperature, n layer temperatures.  jac_out: [member][(n+1)][2], i.e. per member the
+   reference's default column-major 2 x (n+1) Jacobian (dependent index fastest). */
+int ref_ensemble_radiances(int64_t n_members, int n, const double* state, double* jac_out, int n_threads,
+                           double* seconds) {
+  int failed = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+#ifdef _OPENMP
+  const int nt = n_threads > 0 ? n_threads : omp_get_num_procs();
+#pragma omp parallel for schedule(static) num_threads(nt)
+#endif
+  for (int64_t b = 0; b < n_members; ++b) {
+    try {
+      const double* x = state + b * (n + 1);
+      Real rad[2], dst[2];
+      std::vector<Real> dt(2 * n);
+      simulate_radiances(n, x[0], x + 1, rad, dst, &dt[0]);
+      double* j = jac_out + b * 2 * (n + 1);
+      j[0] = dst[0]; j[1] = dst[1];
+      for (int i = 0; i < n; ++i) { j[2 + 2 * i] = dt[2 * i]; j[3 + 2 * i] = dt[2 * i + 1]; }
+    } catch (...) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+      failed = 1;
+    }
+  }
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return failed;
 }
 
 /* RosenbrockN of test/test_minimizer.cpp:39-49 and :103-108: y = calc_y(x);

@@ -89,3 +89,26 @@ def test_zz_helper_feeds_the_batch_entry_point(po, tmp_path, n_members):
         for mode, got in ((1, d["jac_rev"]), (0, d["jac_fwd"])):
             rc, want = po.jacobian(d["stmt"], m, d["idx"], d["G"], d["indep"], d["dep"], mode)
             assert rc == 0 and same_bits(got[b], want), (mode, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(B_DIR, "ensemble_bench")), reason="ensemble_bench not built")
+@pytest.mark.parametrize("n_members,chunks", [(300, 4), (5003, 1), (5003, 4)])
+def test_zz_radiance_ensemble_end_to_end_every_member(po, n_members, chunks):
+    """BASELINE config 3 end to end (bench.py --workload ensemble1e5 at a smaller size): the reference's radiance model
+    recorded for every member with real Adept templates on all host cores, packed into page-locked memory, replayed
+    by the pipelined batch entry point on every visible GPU -- EVERY member's 2x26 Jacobian must equal, bit for bit,
+    what the reference's own simulate_radiances() (record + Stack::jacobian) returns for that state vector."""
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    if not (po.ref_available("") and hasattr(po._ref(""), "ref_ensemble_radiances")):
+        pytest.skip("oracle/_ref without ref_ensemble_radiances")
+    state = bench.ensemble_state(n_members, seed=n_members)
+    want, _ = po.ref_ensemble_radiances(state, 0, "")
+    for n_dev in sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()}):
+        jac, info = bench.run_ensemble_bench(state, n_dev, reps=1, chunks=chunks)
+        assert jac is not None, info
+        assert jac.shape == (n_members, 26, 2) and info["devices"] == n_dev
+        assert same_bits(jac, want), f"{n_dev} device(s)"
