@@ -232,6 +232,57 @@ __device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, i
   }
 }
 
+// One statement, the whole warp: lanes share its operands (any number of them) and its LHS.  Returns its local step.
+__device__ __forceinline__ int32_t window_walk_one(SlotEntry* T, uint32_t mask, const int32_t* __restrict__ idx, int64_t o0,
+                                                   int64_t o1, int32_t lhs, int lane) {
+  const int64_t nops = o1 - o0;
+  int32_t lv = 1;
+  if (nops < 32) {
+    // one pass: lane < nops handles an operand, lane == nops the LHS
+    const int32_t x = (lane < nops) ? idx[o0 + lane] : (lane == nops ? lhs : -1);
+    SlotEntry* e = nullptr;
+    if (x >= 0) {
+      int32_t wl, rl;
+      e = table_entry(T, mask, x, wl, rl);
+      lv = (lane < nops) ? max(wl + 1, rl)          // RAW (strict), MONO (non-strict); empty = -1
+                         : max(wl, rl) + 1;         // WAW, WAR (strict)
+      lv = max(lv, 1);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+    if (lane < nops) __stcg(&e->rl, lv);            // lv >= the old rl by MONO
+    __syncwarp();
+    if (lane == nops) __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(lv, 0));   // the write retires the old version and its readers
+  } else {
+    for (int64_t o = o0 + lane; o < o1; o += 32) {
+      int32_t wl, rl;
+      table_entry(T, mask, idx[o], wl, rl);
+      lv = max(lv, max(wl + 1, rl));
+    }
+    int32_t wl, rl;
+    SlotEntry* eL = table_entry(T, mask, lhs, wl, rl);
+    lv = max(lv, max(wl, rl) + 1);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+    __syncwarp();
+    for (int64_t o = o0 + lane; o < o1; o += 32) {
+      int32_t a, b;
+      SlotEntry* e = table_entry(T, mask, idx[o], a, b);
+      __stcg(&e->rl, lv);
+    }
+    __syncwarp();
+    if (lane == 0) __stcg(reinterpret_cast<int2*>(&eL->wl), make_int2(lv, 0));
+  }
+  __syncwarp();
+  return lv;
+}
+
+// The walk of a window is a chain of dependent table look-ups, one L2/DRAM round trip per statement (the tables of
+// all windows together are far larger than L2).  Consecutive statements rarely touch a common slot, so the warp
+// looks up FOUR statements at a time -- eight lanes each: up to seven operands and the LHS -- and commits the longest
+// prefix of them that is conflict-free: a statement that shares ANY slot with an earlier statement of the batch
+// (found with one match.any over the 32 slot ids) must see that statement's updates, so it and its successors are
+// looked up again in the next round.  The result is exactly that of the one-at-a-time walk (oracle_levels mode 2).
 __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restrict__ stmt, int64_t n_stmt,
                                                             const int32_t* __restrict__ idx,
                                                             const int64_t* __restrict__ win_lo,
@@ -252,61 +303,63 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   }
   SlotEntry* T = tables + tab_off[w];
   const uint32_t mask = static_cast<uint32_t>(tab_off[w + 1] - tab_off[w]) - 1u;
+  const int g = lane >> 3, q = lane & 7;
+  const uint32_t lower = (g == 0) ? 0u : ((1u << (g * 8)) - 1u);   // the lanes of the groups before mine
   int32_t depth = 0;
-  int64_t o0 = stmt[lo - 1].y;
-  int2 st = stmt[lo];
-  for (int64_t s = lo; s <= hi; ++s) {
-    const int64_t o1 = st.y;
-    const int32_t lhs = st.x;
-    const int64_t nops = o1 - o0;
-    const int2 st_next = (s < hi) ? stmt[s + 1] : st;  // prefetch: independent of the table work below
-    int32_t lv = 1;
-    if (nops < 32) {
-      // one pass: lane < nops handles an operand, lane == nops the LHS
-      const int32_t x = (lane < nops) ? idx[o0 + lane] : (lane == nops ? lhs : -1);
-      SlotEntry* e = nullptr;
-      if (x >= 0) {
-        int32_t wl, rl;
-        e = table_entry(T, mask, x, wl, rl);
-        lv = (lane < nops) ? max(wl + 1, rl)          // RAW (strict), MONO (non-strict); empty = -1
-                           : max(wl, rl) + 1;         // WAW, WAR (strict)
-        lv = max(lv, 1);
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-      if (lane < nops) __stcg(&e->rl, lv);            // lv >= the old rl by MONO
-      __syncwarp();
-      if (lane == nops) {                             // the write retires the old version and its readers
-        __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(lv, 0));
-        level[s] = lv;
-      }
-    } else {
-      for (int64_t o = o0 + lane; o < o1; o += 32) {
-        int32_t wl, rl;
-        table_entry(T, mask, idx[o], wl, rl);
-        lv = max(lv, max(wl + 1, rl));
-      }
+  int32_t o0 = stmt[lo - 1].y;     // operation offsets fit 32 bits (n_ops + n_statements < 2^31)
+  int64_t s = lo;
+  while (s <= hi) {
+    const int64_t sg = s + g;
+    int2 st = make_int2(0, 0);
+    if (q == 0 && sg <= hi) st = stmt[sg];
+    const int32_t e0 = __shfl_sync(0xffffffffu, st.y, 0), e1 = __shfl_sync(0xffffffffu, st.y, 8),
+                  e2 = __shfl_sync(0xffffffffu, st.y, 16), e3 = __shfl_sync(0xffffffffu, st.y, 24);
+    const int32_t ob = g == 0 ? o0 : (g == 1 ? e0 : (g == 2 ? e1 : e2));
+    const int32_t oe = g == 0 ? e0 : (g == 1 ? e1 : (g == 2 ? e2 : e3));
+    const int32_t nops = oe - ob;
+    const int32_t lhs = __shfl_sync(0xffffffffu, st.x, g * 8);
+    const uint32_t okm = __ballot_sync(0xffffffffu, q == 0 && sg <= hi && nops <= 7);
+    const int ngrp = (okm & 1u) ? ((okm >> 8 & 1u) ? ((okm >> 16 & 1u) ? ((okm >> 24 & 1u) ? 4 : 3) : 2) : 1) : 0;
+    if (ngrp == 0) {   // statement s has eight operands or more: the whole warp takes it
+      const int32_t lhs0 = __shfl_sync(0xffffffffu, st.x, 0);
+      const int32_t lv = window_walk_one(T, mask, idx, o0, e0, lhs0, lane);
+      if (lane == 0) level[s] = lv;
+      depth = max(depth, lv);
+      o0 = e0;
+      ++s;
+      continue;
+    }
+    int32_t x = -1;
+    if (g < ngrp) x = q < nops ? idx[ob + q] : (q == nops ? lhs : -1);
+    SlotEntry* e = nullptr;
+    int32_t v = 1;
+    if (x >= 0) {
       int32_t wl, rl;
-      SlotEntry* eL = table_entry(T, mask, lhs, wl, rl);
-      lv = max(lv, max(wl, rl) + 1);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-      __syncwarp();
-      for (int64_t o = o0 + lane; o < o1; o += 32) {
-        int32_t a, b;
-        SlotEntry* e = table_entry(T, mask, idx[o], a, b);
-        __stcg(&e->rl, lv);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        __stcg(reinterpret_cast<int2*>(&eL->wl), make_int2(lv, 0));
-        level[s] = lv;
-      }
+      e = table_entry(T, mask, x, wl, rl);
+      v = (q < nops) ? max(wl + 1, rl) : max(wl, rl) + 1;
+      v = max(v, 1);
+    }
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));   // the statement's step, in all eight lanes of its group
+    const uint32_t same = __match_any_sync(0xffffffffu, x);
+    const uint32_t cm = __ballot_sync(0xffffffffu, x >= 0 && (same & lower) != 0u);
+    int ncommit = ngrp;
+    if (cm) ncommit = min(ncommit, (__ffs(cm) - 1) >> 3);   // the first group that shares a slot with an earlier one (>= 1)
+    const bool commit = g < ncommit;
+    if (commit && x >= 0 && q < nops) __stcg(&e->rl, v);                    // readers of the live version
+    __syncwarp();
+    if (commit && q == nops) {                                               // the write retires the old version and its readers
+      __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(v, 0));
+      level[sg] = v;
     }
     __syncwarp();
-    depth = max(depth, lv);
-    o0 = o1;
-    st = st_next;
+    int32_t vm = commit ? v : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, d));
+    depth = max(depth, vm);
+    o0 = ncommit == 1 ? e0 : (ncommit == 2 ? e1 : (ncommit == 3 ? e2 : e3));
+    s += ncommit;
   }
   if (lane == 0) win_depth[w] = depth;
 }

@@ -266,6 +266,51 @@ def ensemble_workload(args, eng, pkg, po, W, K):
             "note": info["stdout"]}
 
 
+def checkpoint_workload(args, po, K):
+    """the reference's checkpointing example at its own size (test/test_checkpoint.cpp:52-56: NX=100,
+    100 blocks of 100 Toon steps), recorded with real Adept templates by adept-2_b200/dropin/_build/chain_check:
+    (a) the reference's loop through the drop-in Stack (every reverse() a GPU sweep with host gradient vectors),
+    (b) the device-resident chain (adept_cuda_chain_*), against the CPU sweeps of the same block tapes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tempfile
+    import pathlib
+    from test_chain_helper import EXE, run_check, oracle_chain
+    if not os.path.exists(EXE):
+        return {"metric": "checkpoint chain", "value": None, "error": "chain_check not built"}
+    nblocks, nt = 100, 100
+    best = None
+    with tempfile.TemporaryDirectory() as d:
+        for _ in range(max(1, min(K, 3)) + 1):
+            r = run_check(pathlib.Path(d), nblocks, nt, "gpu")
+            if best is None or r["ms_chain"] < best["ms_chain"]:
+                best = r
+    t0 = time.perf_counter()
+    want = oracle_chain(po, best["blocks"])
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    ops = sum(b["mult"].size for b in best["blocks"])
+    ok = bool(np.array_equal(best["dj_chain"].view(np.uint64), want.view(np.uint64)) and
+              np.array_equal(best["dj_loop"].view(np.uint64), want.view(np.uint64)))
+    return {"metric": "tape entries per second through a checkpoint chain (reverse sweeps, one per freshly recorded block)",
+            "value": ops / (best["ms_chain"] / 1e3), "unit": "entry/s", "n_gpus": 1, "steps": nblocks, "warmup": 1,
+            "ms_per_step": best["ms_chain"] / nblocks, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"test/test_checkpoint.cpp at its own size: NX=100, {nblocks} blocks x {nt} Toon steps, "
+                                   f"{ops // nblocks} operations per block; recording on the host (real Adept templates) inside the timed region"},
+            "e2e": {"value": ops / (best["ms_chain"] / 1e3), "unit": "entry/s", "ms_per_step": best["ms_chain"] / nblocks,
+                    "h2d_bytes_per_step": int(sum(b["stmt"].nbytes + b["mult"].nbytes + b["idx"].nbytes for b in best["blocks"]) / nblocks),
+                    "d2h_bytes_per_step": 0,
+                    "phases_ms": {"chain_total_ms": best["ms_chain"], "dropin_loop_total_ms": best["ms_loop"],
+                                  "host_recording_ms_in_the_loop_variant": best["ms_record"], "cpu_sweeps_total_ms": cpu_ms},
+                    "verdict": ("At the reference's own size (20 000-statement blocks) the CPU sweeps take %.1f ms in all; the GPU chain takes "
+                                "%.0f ms including %.0f ms of host recording: per block the device-side schedule build and ~600 dependent launches "
+                                "of a 300-step level sweep cost more than the 0.2 ms CPU sweep.  The chain is %.1fx faster than calling the drop-in "
+                                "block by block, and it only pays off against the CPU for blocks of millions of statements."
+                                % (cpu_ms, best["ms_chain"], best["ms_record"], best["ms_loop"] / max(best["ms_chain"], 1e-9)))},
+            "cpu_baseline": {"value": ops / (cpu_ms / 1e3), "unit": "entry/s", "cores": 1, "kind": "port",
+                             "sample": "the same block tapes swept by the oracle's compute_adjoint, hand-off in host memory (no recording time)"},
+            "parity_bit_exact_vs_oracle": ok}
+
+
 def side_workload(args, name):
     """BASELINE configs 5 and 3: not Jacobians of one tape, so they have their own small drivers.
     Printed in the same JSON shape; `value` is from CUDA events around the device work, `e2e` the whole
@@ -354,6 +399,8 @@ def side_workload(args, name):
                 "cpu_baseline": {"value": O / cpu_s, "unit": "entry/s", "cores": 1, "kind": "reference" if rt else "port",
                                  "sample": "the whole sweep, single-threaded by design (adept/Stack.cpp:139-164)"},
                 "parity_bit_exact_vs_oracle": bool(np.array_equal(out.view(np.uint64), want.view(np.uint64)))}
+    elif name == "checkpoint":
+        line = checkpoint_workload(args, po, K)
     else:  # ensemble1e5
         line = ensemble_workload(args, eng, pkg, po, W, K)
     print(json.dumps(line))
@@ -417,7 +464,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="synthetic1e8_fwd", choices=sorted(WORKLOADS) + ["rosenbrock1e7", "ensemble1e5"])
+    ap.add_argument("--workload", default="synthetic1e8_fwd", choices=sorted(WORKLOADS) + ["rosenbrock1e7", "ensemble1e5", "checkpoint"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--reverse-steps", type=int, default=2, help="timed steps of the other sweep direction (workloads that name it)")
@@ -442,7 +489,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload in ("rosenbrock1e7", "ensemble1e5"):
+    if args.workload in ("rosenbrock1e7", "ensemble1e5", "checkpoint"):
         return side_workload(args, args.workload) if rank == 0 else 0
     W = max(args.warmup, 3)
     K = max(args.steps, 1)

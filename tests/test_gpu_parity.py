@@ -165,8 +165,12 @@ def test_tiny_steps_ride_along_with_the_previous_launch(engine, name, tail, stre
 # ---- the device-side dependency analysis ------------------------------------------------------------
 @pytest.mark.parametrize("window", [0, 64, 777, 4096])
 def test_levels_match_the_sequential_rule(engine, po, pkg, window):
+    # the last four have more slots than the shared-memory table holds: hash-table walk, four statements per round --
+    # random slots (hardly any conflict), a stencil (every neighbour conflicts), and a 71996-operand statement
     for t in (pkg.tapegen.advection_tape("toon", 96, 40), pkg.tapegen.synthetic_tape(30000, 11, 64, seed=5),
-              pkg.tapegen.rosenbrock_tape(3000), pkg.tapegen.rosenbrock_tape(18000)):   # the last: a 71996-operand statement
+              pkg.tapegen.rosenbrock_tape(3000), pkg.tapegen.rosenbrock_tape(18000),
+              pkg.tapegen.synthetic_tape(150000, 16, 64, seed=9), pkg.tapegen.advection_tape("toon", 8000, 4),
+              pkg.tapegen.advection_tape("lw", 7000, 3)):
         upload(engine, t, LEVELS, window)
         got = engine.levels()
         W = window or 65536
