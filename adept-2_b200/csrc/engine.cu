@@ -46,6 +46,7 @@ constexpr double kWideStepCtas = 4096.0;              // average CTAs per step a
 constexpr size_t kStageBytes = size_t(32) << 20;      // pinned staging buffer for pageable uploads (two of them)
 constexpr size_t kPoolKeepBytes = size_t(8) << 30;    // analysis temporaries kept between uploads up to this size
 constexpr int64_t kTailItems = 4;                     // (chunks x column groups) up to which a step rides along as a tail
+constexpr int kFwdCbsDefault = 16;                    // forward_balanced_kernel: column blocks per CTA (kFwdCbs = 32 is the limit)
 constexpr size_t kPoolSlots = 48;                     // analysis temporaries (Shard::pool)
 
 struct Buf {
@@ -1133,9 +1134,10 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const bool balanced = c->opt_fwd_balanced != 0;
     // balanced kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
     // groups are kept for the streams below
-    int cbs = kFwdCbs;
+    // 16 column blocks per CTA (two per warp) measured best on BASELINE config 4's shape: 8 and 16 within 1 %, 32 about 4 % slower
+    int cbs = kFwdCbsDefault;
     if (c->opt_cbs > 0) cbs = int(std::min<int64_t>(c->opt_cbs, kFwdCbs));
-    else if (F.n_colblocks < kFwdCbs * c->opt_streams)
+    else if (F.n_colblocks < kFwdCbsDefault * c->opt_streams)
       cbs = std::max(std::min(8, F.n_colblocks), (F.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
     cbs = std::max(1, std::min(cbs, kFwdCbs));
     F.cbs = cbs;
@@ -1146,10 +1148,12 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const int groups = (all_cb + gwidth - 1) / gwidth;
     int nstr = std::max(1, std::min<int>(c->opt_streams, groups));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= (balanced ? kWideStepCtas / 4 : kWideStepCtas) ||
-        c->opt_time_kernels || c->opt_profile_every)
-      nstr = 1;
+    // wide steps: two direction halves on two streams still pay (the tail of one half's step is filled by the other's
+    // next step: 3 % on config 4's shape); more streams only re-read the record stream
+    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= (balanced ? kWideStepCtas / 4 : kWideStepCtas))
+      nstr = std::min(nstr, balanced ? 2 : 1);
     if (c->opt_wide_streams > 0) nstr = std::max(1, std::min<int>(c->opt_wide_streams, groups));
+    if (c->opt_time_kernels || c->opt_profile_every) nstr = 1;
     s.stat["sweep_streams"] = nstr;
     while (int(s.aux.size()) < nstr - 1) {
       cudaStream_t st;
