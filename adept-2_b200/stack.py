@@ -115,6 +115,12 @@ class Engine:
                                                 idx.shape[0], int(max_gradient), int(epoch)))
         self.tape_shape = (stmt.shape[0], idx.shape[0], int(max_gradient))
 
+    def tape_tag(self):
+        """The caller tag (``epoch``) of the tape this context holds, or None when it holds none."""
+        e = C.c_uint64()
+        rc = self.L.adept_cuda_tape_epoch(self.h, C.byref(e), None, None)
+        return None if rc else int(e.value)
+
     def set_option(self, key: str, value: int):
         self._chk(self.L.adept_cuda_set_option(self.h, key.encode(), int(value)))
 
@@ -207,6 +213,9 @@ class Engine:
         return out
 
 
+_next_tag = 0   # tags of uploaded tapes, unique in this process (0 is never used)
+
+
 class Stack:
     """Mirror of adept::Stack for the replay path (reference include/adept/Stack.h:97-808)."""
 
@@ -229,6 +238,7 @@ class Stack:
         self._dependent = []
         self._epoch = 0
         self._uploaded = None
+        self._tag = None
         self.new_recording()
 
     @property
@@ -351,10 +361,16 @@ class Stack:
 
     # -- replay: everything below runs on the GPU --------------------------------------------
     def _sync_tape(self):
+        """Upload when this Stack's tape changed -- or when the ENGINE no longer holds it: an Engine holds one tape,
+        and another Stack sharing the engine (or an ensemble / chain call) may have replaced ours.  Every upload gets
+        a process-unique tag that the engine hands back (adept_cuda_tape_epoch)."""
+        global _next_tag
         key = (self._epoch, self._n_stmt, self._n_ops, self._max_gradient)
-        if self._uploaded != key:
+        if self._uploaded != key or self._engine.tape_tag() != self._tag:
+            _next_tag += 1
+            self._tag = _next_tag
             self._engine.upload_tape(self._stmt[: self._n_stmt], self._mult[: self._n_ops],
-                                     self._idx[: self._n_ops], self._max_gradient, epoch=self._epoch)
+                                     self._idx[: self._n_ops], self._max_gradient, epoch=self._tag)
             self._uploaded = key
 
     def compute_adjoint(self, flags: int = 0):

@@ -182,13 +182,19 @@ void  adept_cuda_host_free(void* p);
                      the next adept_cuda_upload_tape
      "fused"         1 (default) = the level-scheduled reverse sweep runs ONE kernel per step over versioned rows
                      (two workspace rows per slot, no snapshot buffer); 0 = snapshot + gather, two kernels per step
-     "cbs"           fused kernel: 64-direction column blocks per CTA (1..32; 0 = automatic)
+     "cbs"           fused reverse kernel and balanced forward kernel: 64-direction column blocks per CTA (1..32; 0 = automatic:
+                     32 reverse, 16 forward, fewer when a device holds few directions)
      "tail"          fused kernel: 1 (default) = steps of a chunk or two are run by the last CTA of the previous step's
                      launch instead of a launch of their own
      "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
                      between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
                      (stats "dominant_ms", "dominant_launches"); off by default
+     "fwd_balanced"  1 (default) = the level-scheduled forward sweep uses forward_balanced_kernel (a CTA owns a chunk and
+                     up to 32 column blocks, its warps take the active ones in turn and walk a compacted list) for every step
+                     whose chunks fit one staged piece; 0 = forward_level_kernel (warp bound to a column block) throughout
+     "wide_streams"  N > 0: spread the forward level sweep over N streams even when its steps are wide (default 0: two
+                     streams on wide steps, "streams" on narrow ones)
      "batch_chunks"  adept_cuda_jacobian_batch: chunks per device through its copy-in / sweep / copy-out pipeline (1..64,
                      default 4; a chunk holds at least 256 members)
      "remove_null"   1 = tape compaction on upload: operations whose multiplier is zero are dropped, as a reference built

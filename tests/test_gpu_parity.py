@@ -427,6 +427,25 @@ def test_stack_api(pkg, po):
     assert s2.jacobian().tolist() == [20.0, 30.0]
 
 
+def test_two_stacks_sharing_one_engine(pkg):
+    """an Engine holds ONE tape; a Stack must notice that another Stack (or an ensemble call) on the
+    same engine replaced it, and upload again instead of replaying the stranger's tape."""
+    eng = pkg.Engine([0])
+    a, b = pkg.Stack(engine=eng), pkg.Stack(engine=eng)
+    for s, m in ((a, 2.0), (b, 5.0)):
+        x = s.register_gradient(); y = s.register_gradient()
+        s.new_recording()
+        s.push_rhs(m, x); s.push_lhs(y)
+        s.independent(x); s.dependent(y)
+    assert a.jacobian().tolist() == [2.0]
+    assert b.jacobian().tolist() == [5.0]
+    assert a.jacobian().tolist() == [2.0]          # a's tape was replaced by b's in between
+    t = pkg.tapegen.radiance_tape()
+    eng.jacobian_batch(1, t["stmt"], t["idx"], t["max_gradient"], t["mult"][:, None] * np.ones((1, 3)), t["indep"], t["dep"])
+    assert b.jacobian().tolist() == [5.0]          # ... and by the ensemble's structure
+    eng.close()
+
+
 # ---- ensembles: B tapes sharing one structure (BASELINE config 3: simulate_radiances x 1e5 members) ----
 @pytest.mark.parametrize("B", [1, 37, 1000])
 def test_ensemble_jacobians(engine, po, pkg, B):
