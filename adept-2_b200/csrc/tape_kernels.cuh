@@ -278,11 +278,60 @@ __device__ __forceinline__ int32_t window_walk_one(SlotEntry* T, uint32_t mask, 
 }
 
 // The walk of a window is a chain of dependent table look-ups, one L2/DRAM round trip per statement (the tables of
-// all windows together are far larger than L2).  Consecutive statements rarely touch a common slot, so the warp
-// looks up FOUR statements at a time -- eight lanes each: up to seven operands and the LHS -- and commits the longest
-// prefix of them that is conflict-free: a statement that shares ANY slot with an earlier statement of the batch
-// (found with one match.any over the 32 slot ids) must see that statement's updates, so it and its successors are
-// looked up again in the next round.  The result is exactly that of the one-at-a-time walk (oracle_levels mode 2).
+// all windows together are far larger than L2).  Two things shorten the chain:
+//   * Consecutive statements rarely touch a common slot, so the warp looks up FOUR statements at a time -- eight lanes
+//     each: up to seven operands and the LHS -- and commits the longest prefix of them that is conflict-free: a
+//     statement that shares ANY slot with an earlier statement of the round (found with one match.any over the 32
+//     slot ids) must see that statement's updates, so it and its successors are looked up again in the next round.
+//   * The statements and operand slots of the next two rounds are already in registers (a sliding window of twelve
+//     statements in three tiers of four, refilled by loads that are issued BEHIND the round's table probe), so the
+//     only memory latency on the critical path of a round is the probe itself.
+// The result is exactly that of the one-at-a-time walk (oracle_levels mode 2).
+struct WalkTier {
+  int32_t lhs, beg, end, x;   // the statement of my group; x = the slot my lane looks up (-1: none)
+  bool ok;                    // the statement exists and has at most seven operands
+  bool exists;
+};
+// statements base+g (g = 0..3) -> a tier; prev_end = end of statement base-1 (ignored when base-1 does not exist)
+__device__ __forceinline__ WalkTier walk_load_tier(const int2* __restrict__ stmt, const int32_t* __restrict__ idx, int64_t base,
+                                                   int64_t hi, int32_t prev_end, int g, int q) {
+  WalkTier t;
+  const int64_t sg = base + g;
+  int2 st = make_int2(0, prev_end);
+  if (q == 0 && sg <= hi) st = stmt[sg];
+  const int32_t e0 = __shfl_sync(0xffffffffu, st.y, 0), e1 = __shfl_sync(0xffffffffu, st.y, 8),
+                e2 = __shfl_sync(0xffffffffu, st.y, 16);
+  t.exists = sg <= hi;
+  t.lhs = __shfl_sync(0xffffffffu, st.x, g * 8);
+  t.end = __shfl_sync(0xffffffffu, st.y, g * 8);
+  t.beg = g == 0 ? prev_end : (g == 1 ? e0 : (g == 2 ? e1 : e2));
+  const int32_t nops = t.end - t.beg;
+  t.ok = t.exists && nops <= 7;
+  t.x = -1;
+  if (t.ok) t.x = q < nops ? idx[t.beg + q] : (q == nops ? t.lhs : -1);
+  return t;
+}
+__device__ __forceinline__ WalkTier walk_pick(const WalkTier& a, const WalkTier& b, int j, int q) {
+  // tier entry number j of the concatenation (a, b): groups 0..3 from a, 4..7 from b
+  const int src = ((j & 3) << 3) + q;
+  WalkTier r;
+  const bool hi4 = j >= 4;
+  const int32_t la = __shfl_sync(0xffffffffu, a.lhs, src), lb = __shfl_sync(0xffffffffu, b.lhs, src);
+  const int32_t ba = __shfl_sync(0xffffffffu, a.beg, src), bb = __shfl_sync(0xffffffffu, b.beg, src);
+  const int32_t ea = __shfl_sync(0xffffffffu, a.end, src), eb = __shfl_sync(0xffffffffu, b.end, src);
+  const int32_t xa = __shfl_sync(0xffffffffu, a.x, src), xb = __shfl_sync(0xffffffffu, b.x, src);
+  const int fa = __shfl_sync(0xffffffffu, (a.ok ? 1 : 0) | (a.exists ? 2 : 0), src);
+  const int fb = __shfl_sync(0xffffffffu, (b.ok ? 1 : 0) | (b.exists ? 2 : 0), src);
+  r.lhs = hi4 ? lb : la;
+  r.beg = hi4 ? bb : ba;
+  r.end = hi4 ? eb : ea;
+  r.x = hi4 ? xb : xa;
+  const int f = hi4 ? fb : fa;
+  r.ok = f & 1;
+  r.exists = f & 2;
+  return r;
+}
+
 __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restrict__ stmt, int64_t n_stmt,
                                                             const int32_t* __restrict__ idx,
                                                             const int64_t* __restrict__ win_lo,
@@ -306,37 +355,53 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   const int g = lane >> 3, q = lane & 7;
   const uint32_t lower = (g == 0) ? 0u : ((1u << (g * 8)) - 1u);   // the lanes of the groups before mine
   int32_t depth = 0;
-  int32_t o0 = stmt[lo - 1].y;     // operation offsets fit 32 bits (n_ops + n_statements < 2^31)
   int64_t s = lo;
+  bool warm = false;
+  WalkTier c, n;   // statements s..s+3 and s+4..s+7
+  int32_t o0 = stmt[lo - 1].y;   // end of statement s-1 (operation offsets fit 32 bits: n_ops + n_statements < 2^31)
   while (s <= hi) {
-    const int64_t sg = s + g;
-    int2 st = make_int2(0, 0);
-    if (q == 0 && sg <= hi) st = stmt[sg];
-    const int32_t e0 = __shfl_sync(0xffffffffu, st.y, 0), e1 = __shfl_sync(0xffffffffu, st.y, 8),
-                  e2 = __shfl_sync(0xffffffffu, st.y, 16), e3 = __shfl_sync(0xffffffffu, st.y, 24);
-    const int32_t ob = g == 0 ? o0 : (g == 1 ? e0 : (g == 2 ? e1 : e2));
-    const int32_t oe = g == 0 ? e0 : (g == 1 ? e1 : (g == 2 ? e2 : e3));
-    const int32_t nops = oe - ob;
-    const int32_t lhs = __shfl_sync(0xffffffffu, st.x, g * 8);
-    const uint32_t okm = __ballot_sync(0xffffffffu, q == 0 && sg <= hi && nops <= 7);
+    if (!warm) {
+      c = walk_load_tier(stmt, idx, s, hi, o0, g, q);
+      n = walk_load_tier(stmt, idx, s + 4, hi, __shfl_sync(0xffffffffu, c.end, 24), g, q);
+      warm = true;
+    }
+    const uint32_t okm = __ballot_sync(0xffffffffu, q == 0 && c.ok);
     const int ngrp = (okm & 1u) ? ((okm >> 8 & 1u) ? ((okm >> 16 & 1u) ? ((okm >> 24 & 1u) ? 4 : 3) : 2) : 1) : 0;
     if (ngrp == 0) {   // statement s has eight operands or more: the whole warp takes it
-      const int32_t lhs0 = __shfl_sync(0xffffffffu, st.x, 0);
-      const int32_t lv = window_walk_one(T, mask, idx, o0, e0, lhs0, lane);
+      const int32_t b0 = __shfl_sync(0xffffffffu, c.beg, 0), e0 = __shfl_sync(0xffffffffu, c.end, 0);
+      const int32_t lhs0 = __shfl_sync(0xffffffffu, c.lhs, 0);
+      const int32_t lv = window_walk_one(T, mask, idx, b0, e0, lhs0, lane);
       if (lane == 0) level[s] = lv;
       depth = max(depth, lv);
       o0 = e0;
       ++s;
+      warm = false;
       continue;
     }
-    int32_t x = -1;
-    if (g < ngrp) x = q < nops ? idx[ob + q] : (q == nops ? lhs : -1);
+    // 1. the round's table probe goes out first ...
+    const int32_t x = (g < ngrp) ? c.x : -1;
+    uint32_t h = 0;
+    int4 probe = make_int4(-1, 0, -1, -1);
+    if (x >= 0) {
+      h = slot_hash(x) & mask;
+      probe = __ldcg(reinterpret_cast<const int4*>(&T[h]));
+    }
+    // 2. ... then the loads that refill the window two rounds ahead (statements s+8..s+11 and their operand slots)
+    const WalkTier f = walk_load_tier(stmt, idx, s + 8, hi, __shfl_sync(0xffffffffu, n.end, 24), g, q);
+    // 3. the probe's answer (open addressing: walk on from h when the first entry belongs to another slot)
     SlotEntry* e = nullptr;
     int32_t v = 1;
     if (x >= 0) {
       int32_t wl, rl;
-      e = table_entry(T, mask, x, wl, rl);
-      v = (q < nops) ? max(wl + 1, rl) : max(wl, rl) + 1;
+      if (probe.x == x) {
+        e = &T[h];
+        wl = probe.z;
+        rl = probe.w;
+      } else {
+        e = table_entry(T, mask, x, wl, rl);
+      }
+      const int32_t nops = c.end - c.beg;
+      v = (q < nops) ? max(wl + 1, rl) : max(wl, rl) + 1;   // RAW (strict), MONO (non-strict) | WAW, WAR (strict)
       v = max(v, 1);
     }
     v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -347,18 +412,24 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     int ncommit = ngrp;
     if (cm) ncommit = min(ncommit, (__ffs(cm) - 1) >> 3);   // the first group that shares a slot with an earlier one (>= 1)
     const bool commit = g < ncommit;
-    if (commit && x >= 0 && q < nops) __stcg(&e->rl, v);                    // readers of the live version
+    const int32_t my_nops = c.end - c.beg;
+    if (commit && x >= 0 && q < my_nops) __stcg(&e->rl, v);                 // readers of the live version
     __syncwarp();
-    if (commit && q == nops) {                                               // the write retires the old version and its readers
+    if (commit && q == my_nops) {                                            // the write retires the old version and its readers
       __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(v, 0));
-      level[sg] = v;
+      level[s + g] = v;
     }
     __syncwarp();
     int32_t vm = commit ? v : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, d));
     depth = max(depth, vm);
-    o0 = ncommit == 1 ? e0 : (ncommit == 2 ? e1 : (ncommit == 3 ? e2 : e3));
+    // 4. slide the window by the statements that were committed
+    const WalkTier c2 = walk_pick(c, n, ncommit + g, q);
+    const WalkTier n2 = walk_pick(n, f, ncommit + g, q);      // entry (ncommit + 4 + g) of (c, n, f) = entry (ncommit + g) of (n, f)
+    o0 = __shfl_sync(0xffffffffu, c.end, (ncommit - 1) * 8);
+    c = c2;
+    n = n2;
     s += ncommit;
   }
   if (lane == 0) win_depth[w] = depth;
