@@ -189,6 +189,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_coop_pack = 1;      // window packing as one cooperative kernel (0: three launches per window)
   int opt_batch_chunks = 4;   // ensemble entry point: chunks per device through the copy-in / sweep / copy-out pipeline
   int opt_wide_streams = 0;   // > 0: this many streams for the forward level sweep even when its steps are wide (experiments)
   int opt_fwd_balanced = 1;   // forward level sweep: balanced CTA shape (forward_balanced_kernel); 0: forward_level_kernel only
@@ -566,7 +567,42 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     CK(cudaMemsetAsync(gw.p, 0, size_t(s.max_gradient) * 4, s.stream));
     CK(cudaMemsetAsync(gr.p, 0, size_t(s.max_gradient) * 4, s.stream));
     CK(cudaMemsetAsync(need.p, 0, size_t(total_depth + 1) * 4, s.stream));
-    for (int64_t w = 0; w < n_windows; ++w) {
+    // the whole pass as one cooperative kernel (tape_kernels.cuh, window_pack_kernel); the per-window launches below
+    // remain as the fallback when a cooperative launch is not possible (option "coop_pack" = 0 forces them: tests)
+    bool packed = false;
+    if (c->opt_coop_pack) {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_pack_kernel, 256, 0) == cudaSuccess && per_sm >= 1) {
+        PackArgs PA;
+        PA.stmt = s.stmt.as<int2>();
+        PA.idx = s.idx.as<int32_t>();
+        PA.win_lo = win_lo.as<int64_t>();
+        PA.win_op = wopl.as<int64_t>();
+        PA.win_base = wbase.as<int32_t>();
+        PA.tab_off = tab_off.as<int64_t>();
+        PA.tables = tables.as<SlotEntry>();
+        PA.wstate = wstate.as<int2>();
+        PA.max_gradient = s.max_gradient;
+        PA.n_windows = n_windows;
+        PA.level = s.level.as<int32_t>();
+        PA.gw = gw.as<int32_t>();
+        PA.gr = gr.as<int32_t>();
+        PA.need = need.as<int32_t>();
+        PA.gmap = gmap.as<int32_t>();
+        PA.dense = dense ? 1 : 0;
+        void* args[] = {&PA};
+        const unsigned grid = unsigned(s.sm_count * std::min(per_sm, 2));
+        if (cudaLaunchCooperativeKernel((void*)window_pack_kernel, dim3(grid), dim3(256), args, 0, s.stream) == cudaSuccess) {
+          packed = true;
+          s.launches += 1;
+        } else {
+          cudaGetLastError();
+        }
+      } else {
+        cudaGetLastError();
+      }
+    }
+    for (int64_t w = 0; w < n_windows && !packed; ++w) {
       const int64_t lo = h_lo[w], hi = h_lo[w + 1] - 1, o0 = h_op[w], o1 = h_op[w + 1];
       const int32_t depth = h_base[w + 1] - h_base[w];
       int32_t* need_w = need.as<int32_t>() + h_base[w];
@@ -2751,6 +2787,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "coop_pack") {
+    c->opt_coop_pack = value ? 1 : 0;
   } else if (k == "batch_chunks") {
     if (value < 1 || value > 64) return fail(errp, ADEPT_CUDA_ERR_ARG, "batch_chunks must be in 1..64");
     c->opt_batch_chunks = int(value);

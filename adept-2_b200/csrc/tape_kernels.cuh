@@ -685,6 +685,130 @@ __global__ void window_update_kernel(const SlotEntry* __restrict__ T, int64_t ca
     }
   }
 }
+// The whole packing pass as ONE cooperative kernel: windows in order, two grid-wide barriers per window
+// (need | barrier | map (every CTA, redundantly, for itself) + update | barrier) instead of three dependent launches
+// from the host.  Same arithmetic as window_need_kernel / window_map_kernel / window_update*_kernel above.
+struct PackArgs {
+  const int2* stmt;
+  const int32_t* idx;
+  const int64_t* win_lo;    // [n_windows+1] first statement of each window
+  const int64_t* win_op;    // [n_windows+1] first operation of each window
+  const int32_t* win_base;  // [n_windows+1] first entry of each window in need/gmap
+  const int64_t* tab_off;   // [n_windows+1] hash-table offsets (hash variant)
+  const SlotEntry* tables;  // hash variant
+  const int2* wstate;       // dense variant: [n_windows][max_gradient]
+  int64_t max_gradient;
+  int64_t n_windows;
+  const int32_t* level;     // local steps
+  int32_t* gw;
+  int32_t* gr;
+  int32_t* need;
+  int32_t* gmap;
+  int dense;
+};
+
+__global__ void __launch_bounds__(256) window_pack_kernel(PackArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int32_t sneed[kNeedSmem];   // phase A: the CTA's maxima; phase B/C: this window's local -> global step map
+  const int64_t gtid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t gsize = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t w = 0; w < A.n_windows; ++w) {
+    const int64_t lo = A.win_lo[w], hi = A.win_lo[w + 1] - 1, o0 = A.win_op[w], o1 = A.win_op[w + 1];
+    const int32_t base = A.win_base[w], depth = A.win_base[w + 1] - base;
+    int32_t* need = A.need + base;
+    int32_t* gmap = A.gmap + base;
+    const int ns = depth < kNeedSmem ? depth : kNeedSmem;
+    // ---- A. need[l-1] = the largest lower bound earlier windows impose on a statement of local step l ----
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) sneed[k] = 0;
+    __syncthreads();
+    const int64_t n_ops = o1 - o0, total = n_ops + (hi - lo + 1);
+    for (int64_t t = gtid; t < total; t += gsize) {
+      int32_t bound, l;
+      if (t < n_ops) {
+        const int64_t o = o0 + t;
+        const int64_t s = stmt_of_op_range(A.stmt, lo, hi, o);
+        const int32_t x = A.idx[o];
+        bound = max(__ldcg(&A.gw[x]) + 1, __ldcg(&A.gr[x]));   // written by other SMs in the previous window's phase C
+        l = A.level[s];
+      } else {
+        const int64_t s = lo + (t - n_ops);
+        const int32_t x = A.stmt[s].x;
+        bound = max(__ldcg(&A.gw[x]), __ldcg(&A.gr[x])) + 1;
+        l = A.level[s];
+      }
+      if (bound > 1) {
+        if (l <= ns) atomicMax(&sneed[l - 1], bound);
+        else atomicMax(&need[l - 1], bound);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < ns; k += blockDim.x)
+      if (sneed[k] > 1) atomicMax(&need[k], sneed[k]);
+    grid.sync();
+    // ---- B. gmap[l-1] = max(need[l-1], gmap[l-2] + 1): a running maximum of need[l] - l (see window_map_kernel);
+    //         every CTA scans it for itself into shared memory, CTA 0 also publishes it ----
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      int32_t carry = 1;
+      for (int32_t l0 = 0; l0 < depth; l0 += 32) {
+        const int32_t l = l0 + lane;
+        int32_t u = l < depth ? __ldcg(&need[l]) - l : INT32_MIN;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int32_t o = __shfl_up_sync(0xffffffffu, u, d);
+          if (lane >= d) u = max(u, o);
+        }
+        u = max(u, carry);
+        if (l < depth) {
+          if (l < kNeedSmem) sneed[l] = u + l;
+          if (blockIdx.x == 0 || l >= kNeedSmem) gmap[l] = u + l;   // steps beyond the shared table are read back from global
+        }
+        carry = __shfl_sync(0xffffffffu, u, 31);
+      }
+    }
+    __syncthreads();
+    if (depth > kNeedSmem) grid.sync();   // (never with the default window length) readers of gmap[l >= kNeedSmem] wait for every CTA
+    auto G = [&](int32_t l1) -> int32_t { return l1 <= kNeedSmem ? sneed[l1 - 1] : __ldcg(&gmap[l1 - 1]); };
+    // ---- C. fold the window's final per-slot state into the global summary ----
+    if (lo == hi) {
+      // a window of one (huge) statement has no table: its operands are readers at its step, then its LHS is written
+      const int32_t step = G(1);
+      for (int64_t o = o0 + gtid; o < o1; o += gsize) atomicMax(&A.gr[A.idx[o]], step);
+      grid.sync();
+      if (gtid == 0) {
+        const int32_t lhs = A.stmt[lo].x;
+        A.gw[lhs] = step;
+        A.gr[lhs] = 0;
+      }
+    } else if (A.dense) {
+      const int2* state = A.wstate + w * A.max_gradient;
+      for (int64_t x = gtid; x < A.max_gradient; x += gsize) {
+        const int2 e = state[x];
+        if (e.x > 0) {
+          A.gw[x] = G(e.x);
+          A.gr[x] = e.y > 0 ? G(e.y) : 0;
+        } else if (e.y > 0) {
+          A.gr[x] = max(__ldcg(&A.gr[x]), G(e.y));
+        }
+      }
+    } else {
+      const SlotEntry* T = A.tables + A.tab_off[w];
+      const int64_t cap = A.tab_off[w + 1] - A.tab_off[w];
+      for (int64_t i = gtid; i < cap; i += gsize) {
+        const SlotEntry e = T[i];
+        if (e.key < 0) continue;
+        if (e.wl > 0) {   // written in this window: its last writer and the readers after it are what is live now
+          A.gw[e.key] = G(e.wl);
+          A.gr[e.key] = e.rl > 0 ? G(e.rl) : 0;
+        } else if (e.rl > 0) {   // only read: more readers of the version that was already live
+          A.gr[e.key] = max(__ldcg(&A.gr[e.key]), G(e.rl));
+        }
+      }
+    }
+    grid.sync();
+  }
+}
+
 // a window of one (huge) statement has no table: its operands are readers at its step ...
 __global__ void window_update_single_ops_kernel(const int32_t* __restrict__ idx, int64_t o0, int64_t o1,
                                                 const int32_t* __restrict__ gmap, int32_t* __restrict__ gr) {

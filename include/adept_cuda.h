@@ -195,6 +195,8 @@ void  adept_cuda_host_free(void* p);
                      whose chunks fit one staged piece; 0 = forward_level_kernel (warp bound to a column block) throughout
      "wide_streams"  N > 0: spread the forward level sweep over N streams even when its steps are wide (default 0: two
                      streams on wide steps, "streams" on narrow ones)
+     "coop_pack"     1 (default) = the window-packing pass of the dependency analysis runs as ONE cooperative kernel with two
+                     grid-wide barriers per window; 0 = three dependent launches per window from the host
      "batch_chunks"  adept_cuda_jacobian_batch: chunks per device through its copy-in / sweep / copy-out pipeline (1..64,
                      default 4; a chunk holds at least 256 members)
      "remove_null"   1 = tape compaction on upload: operations whose multiplier is zero are dropped, as a reference built

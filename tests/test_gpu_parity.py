@@ -171,12 +171,15 @@ def test_levels_match_the_sequential_rule(engine, po, pkg, window):
               pkg.tapegen.rosenbrock_tape(3000), pkg.tapegen.rosenbrock_tape(18000),
               pkg.tapegen.synthetic_tape(150000, 16, 64, seed=9), pkg.tapegen.advection_tape("toon", 8000, 4),
               pkg.tapegen.advection_tape("lw", 7000, 3)):
-        upload(engine, t, LEVELS, window)
-        got = engine.levels()
         W = window or 65536
         steps, want = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=W, huge=65536, pack=1)
-        assert engine.stat("n_levels") == steps
-        assert np.array_equal(got, want)     # global step of every statement, windows packed
+        for coop in (1, 0):                  # packing as one cooperative kernel, and as three launches per window
+            engine.set_option("coop_pack", coop)
+            upload(engine, t, LEVELS, window)
+            got = engine.levels()
+            assert engine.stat("n_levels") == steps
+            assert np.array_equal(got, want)     # global step of every statement, windows packed
+        engine.set_option("coop_pack", 1)
 
 
 # ---- adversarial little tapes: slot reuse, self reference, repeated operands, empty statements -----
