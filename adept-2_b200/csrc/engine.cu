@@ -372,14 +372,25 @@ int ensure_tape_streams(Shard& s) {
   return 0;
 }
 
-// Releases an oversized pool of analysis temporaries when a builder returns.
+// The analysis temporaries (tens of GB for a 1e8-statement tape: the per-window hash tables, sort buffers) survive the
+// call so that the next upload of a similar tape pays no cudaMalloc/cudaFree (measured: freeing and re-allocating them
+// costs more than the analysis itself).  They are given back when the device runs short of memory -- here, when less
+// than a quarter of it is left, and by the replay drivers when a Jacobian workspace would otherwise need more passes
+// (release_pool).
+size_t pool_bytes(const Shard& s) {
+  size_t total = 0;
+  for (const Buf& b : s.pool) total += b.bytes;
+  return total;
+}
+void release_pool(Shard& s) {
+  for (Buf& b : s.pool) release(b);
+}
 struct PoolGuard {
   Shard& s;
   ~PoolGuard() {
-    size_t total = 0;
-    for (Buf& b : s.pool) total += b.bytes;
-    if (total > kPoolKeepBytes)
-      for (Buf& b : s.pool) release(b);
+    if (pool_bytes(s) <= kPoolKeepBytes) return;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < total_b / 4) release_pool(s);
   }
 };
 
@@ -1569,10 +1580,24 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
     // pass size from the workspace budget
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget =
+    const size_t budget0 =
         c->opt_workspace_bytes > 0 ? size_t(c->opt_workspace_bytes) : size_t(double(free_b + s.g.bytes + s.abuf.bytes) * 0.6);
     // per direction: a gradient column plus (reverse, two-kernel level sweep) a column of the a-snapshot buffer
-    int64_t max_dirs = int64_t(budget / (size_t(n_rows + (fused ? 0 : s.max_step_width)) * 8));
+    const size_t per_dir = size_t(n_rows + (fused ? 0 : s.max_step_width)) * 8;
+    size_t budget = budget0;
+    if (c->opt_workspace_bytes == 0 && pool_bytes(s) > 0) {
+      // would this Jacobian need fewer passes without the kept analysis temporaries?  Then give them back.
+      auto passes = [&](size_t b) {
+        const int64_t md = std::max<int64_t>(32, (int64_t(b / per_dir) / 32) * 32);
+        return (D + md - 1) / md;
+      };
+      if (passes(budget + size_t(double(pool_bytes(s)) * 0.6)) < passes(budget)) {
+        release_pool(s);
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        budget = size_t(double(free_b + s.g.bytes + s.abuf.bytes) * 0.6);
+      }
+    }
+    int64_t max_dirs = int64_t(budget / per_dir);
     max_dirs = (max_dirs / 32) * 32;
     if (max_dirs < 32) max_dirs = 32;
     int64_t pass = std::min<int64_t>(((D + 31) / 32) * 32, max_dirs);
