@@ -75,6 +75,11 @@ struct Shard {
   Buf stmt, mult, idx;
   int64_t n_stmt = 0, n_ops = 0, max_gradient = 0;
   int64_t n_ops_recorded = 0;   // before "remove_null" compaction
+  // the multiplier array may still be on its way (own copy stream) while the level analysis, which reads only
+  // statement_ and index_, already runs: mult_pending until the shard's stream has waited for mult_ev
+  cudaStream_t mult_stream = nullptr;
+  cudaEvent_t mult_ev = nullptr;
+  bool mult_pending = false;
   bool have_tape = false;       // the recorded arrays are on this device
   bool have_schedule = false;   // build_schedule has run for them (validation, level analysis, forward stream)
   bool have_tape_streams = false;
@@ -189,6 +194,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_overlap_upload = 1; // multipliers in page-locked memory are uploaded on their own stream while the level analysis runs
   int opt_coop_pack = 1;      // window packing as one cooperative kernel (0: three launches per window)
   int opt_batch_chunks = 4;   // ensemble entry point: chunks per device through the copy-in / sweep / copy-out pipeline
   int opt_wide_streams = 0;   // > 0: this many streams for the forward level sweep even when its steps are wide (experiments)
@@ -394,6 +400,35 @@ struct PoolGuard {
   }
 };
 
+// The shard's stream waits for an overlapped multiplier upload (adept_cuda_upload_tape), then the multipliers are
+// screened: non-finite values (forward block sparsity is then off) and the fractions equal to 0, +1, -1.
+int settle_multipliers(const adept_cuda_ctx* c, Shard& s) {
+  std::string* errp = &s.err;
+  if (s.mult_pending) {
+    CK(cudaStreamWaitEvent(s.stream, s.mult_ev, 0));
+    s.mult_pending = false;
+  }
+  const int64_t O = s.n_ops;
+  RET(ensure(errp, s.scratch, 64));
+  CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
+  if (O > 0) {
+    validate_kernel<<<grid_for(O, 256, s.sm_count), 256, 0, s.stream>>>(
+        s.stmt.as<int2>(), 0, s.idx.as<int32_t>(), s.mult.as<double>(), O, s.max_gradient, s.scratch.as<int>(),
+        reinterpret_cast<unsigned long long*>(s.scratch.as<char>() + 8));
+    s.launches += 1;
+  }
+  struct { int flags; int pad; unsigned long long n0, n1, nm1; } vh;
+  CK(cudaMemcpyAsync(&vh, s.scratch.p, sizeof vh, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  s.has_nonfinite = (vh.flags & 2) != 0;
+  // Stack::fraction_multipliers_equal_to (include/adept/Stack.h:707-715) for 0, +1, -1, of the tape as recorded
+  s.stat["frac_mult_zero"] = O > 0 ? double(vh.n0) / double(O) : 0.0;
+  s.stat["frac_mult_one"] = O > 0 ? double(vh.n1) / double(O) : 0.0;
+  s.stat["frac_mult_minus_one"] = O > 0 ? double(vh.nm1) / double(O) : 0.0;
+  s.stat["n_zero_multipliers"] = double(vh.n0);
+  return 0;
+}
+
 int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   std::string* errp = &s.err;
   CK(cudaSetDevice(s.dev));
@@ -416,27 +451,28 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     return fail(errp, ADEPT_CUDA_ERR_LIMIT, "tape too long: n_ops + n_statements = %lld >= 2^31", (long long)R);
   const int T = 256;
   auto tp = std::chrono::steady_clock::now();
-  // 1. validate (a bad slot would otherwise be a wild device access); multiplier statistics on the way
+  // 1. validate the STRUCTURE (a bad slot would otherwise be a wild device access).  The multipliers may still be on
+  //    their way (overlapped upload): they are screened later, just before the first kernel that reads them -- unless
+  //    compaction needs them now.
   RET(ensure(errp, s.scratch, 64));
   CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
   validate_kernel<<<grid_for(std::max(O, s.n_stmt), T, s.sm_count), T, 0, s.stream>>>(
-      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), s.mult.as<double>(), O, s.max_gradient, s.scratch.as<int>(),
-      reinterpret_cast<unsigned long long*>(s.scratch.as<char>() + 8));
+      s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), nullptr, O, s.max_gradient, s.scratch.as<int>(), nullptr);
   s.launches += 1;
-  struct { int flags; int pad; unsigned long long n0, n1, nm1; } vh;
-  CK(cudaMemcpyAsync(&vh, s.scratch.p, sizeof vh, cudaMemcpyDeviceToHost, s.stream));
+  int flags = 0;
+  CK(cudaMemcpyAsync(&flags, s.scratch.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
   CK(cudaStreamSynchronize(s.stream));
-  const int flags = vh.flags;
-  s.has_nonfinite = (flags & 2) != 0;
   if (flags & 1)
     return fail(errp, ADEPT_CUDA_ERR_RANGE,
                 "malformed tape: a slot index is outside [0,max_gradient) or statement ends are not monotone");
-  // Stack::fraction_multipliers_equal_to (include/adept/Stack.h:707-715) for 0, +1, -1, of the tape as recorded
-  s.stat["frac_mult_zero"] = O > 0 ? double(vh.n0) / double(O) : 0.0;
-  s.stat["frac_mult_one"] = O > 0 ? double(vh.n1) / double(O) : 0.0;
-  s.stat["frac_mult_minus_one"] = O > 0 ? double(vh.nm1) / double(O) : 0.0;
   s.stat["ops_removed"] = 0.0;
   s.stat["n_ops_recorded"] = double(O);
+  bool mult_settled = false;
+  if (c->opt_remove_null) {
+    RET(settle_multipliers(c, s));
+    mult_settled = true;
+  }
+  struct { unsigned long long n0; } vh = {mult_settled ? (unsigned long long)s.stat["n_zero_multipliers"] : 0ull};
   // 1b. tape compaction (option "remove_null"): drop the zero-multiplier operations, as a reference built with
   //     -DADEPT_REMOVE_NULL_STATEMENTS would have done while recording; everything below sees the compacted tape
   if (c->opt_remove_null && vh.n0 > 0) {
@@ -475,10 +511,15 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   RET(ensure(errp, s.one_chunk, sizeof one_chunk_host));
   CK(cudaMemcpyAsync(s.one_chunk.p, one_chunk_host, sizeof one_chunk_host, cudaMemcpyHostToDevice, s.stream));
   CK(cudaStreamSynchronize(s.stream));  // one_chunk_host is a stack variable
-  if (S == 0) { s.have_schedule = true; return 0; }
+  if (S == 0) {
+    if (!mult_settled) RET(settle_multipliers(c, s));
+    s.have_schedule = true;
+    return 0;
+  }
   s.have_tape_streams = false;
   const bool want_levels = (c->opt_schedule != 1) && (S >= kMinLevelStatements || c->opt_schedule == 2);
   if (!want_levels) {
+    if (!mult_settled) RET(settle_multipliers(c, s));
     RET(ensure_tape_streams(s));
     s.have_schedule = true;
     return 0;
@@ -740,6 +781,10 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       s.fwd_chunk.as<int64_t>(), nullptr, lchunk.as<int64_t>());
   s.launches += 1;
   RET(ensure(errp, s.fwd_l, size_t(R) * sizeof(Rec)));
+  if (!mult_settled) {   // the first reader of the multipliers: wait for an overlapped upload, screen them
+    RET(settle_multipliers(c, s));
+    mult_settled = true;
+  }
   emit_level_streams_kernel<<<grid_for(R, T, s.sm_count), T, 0, s.stream>>>(
       s.stmt.as<int2>(), s.mult.as<double>(), s.idx.as<int32_t>(), v0.as<uint32_t>(), s.foff.as<int64_t>(), S, R,
       s.fwd_l.as<Rec>(), nullptr);
@@ -2080,6 +2125,8 @@ void free_shard(Shard& s) {
     if (s.b_done[q]) cudaEventDestroy(s.b_done[q]);
     if (s.b_out[q]) cudaEventDestroy(s.b_out[q]);
   }
+  if (s.mult_stream) cudaStreamDestroy(s.mult_stream);
+  if (s.mult_ev) cudaEventDestroy(s.mult_ev);
   if (s.bcopy) cudaStreamDestroy(s.bcopy);
   if (s.bback) cudaStreamDestroy(s.bback);
   for (cudaEvent_t e : s.kev) cudaEventDestroy(e);
@@ -2350,12 +2397,32 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   RET(ensure(errp, s.stmt, size_t(n_stmt) * 8));
   RET(ensure(errp, s.mult, size_t(n_ops) * 8));
   RET(ensure(errp, s.idx, size_t(n_ops) * 4));
+  // The level analysis reads only statement_ and index_: when the multipliers sit in page-locked memory (true DMA)
+  // and this context analyses right here, they travel on a stream of their own WHILE the analysis runs; the
+  // shard's stream waits for them just before the first kernel that reads them (settle_multipliers).
+  bool overlap = false;
+  if (n_ops > 0 && !c->multi_process && c->sh.size() == 1 && !c->opt_remove_null && c->opt_overlap_upload) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, multiplier) == cudaSuccess) overlap = (at.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+  }
+  s.mult_pending = false;
   {
     int rc = upload(s, s.stmt.p, statements, size_t(n_stmt) * 8);
-    if (!rc) rc = upload(s, s.mult.p, multiplier, size_t(n_ops) * 8);
     if (!rc) rc = upload(s, s.idx.p, index, size_t(n_ops) * 4);
+    if (!rc && !overlap) rc = upload(s, s.mult.p, multiplier, size_t(n_ops) * 8);
     if (rc) { c->err = s.err; return rc; }
   }
+  if (overlap) {
+    if (!s.mult_stream) {
+      CK(cudaStreamCreateWithFlags(&s.mult_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&s.mult_ev, cudaEventDisableTiming));
+    }
+    CK(cudaMemcpyAsync(s.mult.p, multiplier, size_t(n_ops) * 8, cudaMemcpyHostToDevice, s.mult_stream));
+    CK(cudaEventRecord(s.mult_ev, s.mult_stream));
+    s.mult_pending = true;
+  }
+  c->stat["upload_overlapped"] = overlap ? 1.0 : 0.0;
   CK(cudaStreamSynchronize(s.stream));
   s.n_stmt = n_stmt;
   s.n_ops = n_ops;
@@ -2391,7 +2458,12 @@ int adept_cuda_upload_tape(adept_cuda_ctx* c, const void* statements, int64_t n_
   // Otherwise: now, every local shard on its own host thread.
   if (!c->multi_process) {
     auto t2 = std::chrono::steady_clock::now();
-    RET(over_shards(c, [&](size_t k) -> int { return ensure_schedule(c, c->sh[k]); }));
+    const int brc = over_shards(c, [&](size_t k) -> int { return ensure_schedule(c, c->sh[k]); });
+    if (s.mult_pending) {   // (only when the build failed before reading them) the caller's array must not be in use on return
+      cudaStreamSynchronize(s.mult_stream);
+      s.mult_pending = false;
+    }
+    RET(brc);
     c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
     publish_schedule_stats(c);
     c->stat["analysis_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
@@ -2812,6 +2884,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "overlap_upload") {
+    c->opt_overlap_upload = value ? 1 : 0;
   } else if (k == "coop_pack") {
     c->opt_coop_pack = value ? 1 : 0;
   } else if (k == "batch_chunks") {

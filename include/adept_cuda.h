@@ -195,6 +195,8 @@ void  adept_cuda_host_free(void* p);
                      whose chunks fit one staged piece; 0 = forward_level_kernel (warp bound to a column block) throughout
      "wide_streams"  N > 0: spread the forward level sweep over N streams even when its steps are wide (default 0: two
                      streams on wide steps, "streams" on narrow ones)
+     "overlap_upload" 1 (default) = when the multiplier array is in page-locked memory it is uploaded on a stream of its own
+                     while the level analysis (which reads only statements and indices) already runs; 0 = one after the other
      "coop_pack"     1 (default) = the window-packing pass of the dependency analysis runs as ONE cooperative kernel with two
                      grid-wide barriers per window; 0 = three dependent launches per window from the host
      "batch_chunks"  adept_cuda_jacobian_batch: chunks per device through its copy-in / sweep / copy-out pipeline (1..64,

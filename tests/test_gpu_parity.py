@@ -542,3 +542,37 @@ def test_remove_null_matches_the_reference_built_with_remove_null_statements(eng
             check_jacobians(engine, po, t, "recorded tape")
     finally:
         engine.set_option("remove_null", 0)
+
+
+def test_overlapped_multiplier_upload_from_pinned_memory(engine, po, pkg):
+    """adept_cuda_upload_tape sends page-locked multipliers on a stream of their own while the level analysis (which
+    reads only statements and indices) runs; the first kernel that reads them waits.  Same bits, same statistics,
+    with the overlap on and off, level-scheduled and tape-ordered, with and without compaction."""
+    import torch
+    t = pkg.tapegen.synthetic_tape(300_000, 15, 128, seed=3)
+    t["mult"][::7] = 1.0
+    pin = {k: torch.from_numpy(np.ascontiguousarray(t[k])).pin_memory() for k in ("stmt", "mult", "idx")}
+    rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], t["indep"], t["dep"], 0, n_threads=0)
+    try:
+        for overlap in (1, 0):
+            for schedule in (LEVELS, ORDERED):
+                engine.set_option("overlap_upload", overlap)
+                engine.set_option("schedule", schedule)
+                engine.set_option("smallg", 0)
+                engine.upload_tape(pin["stmt"].numpy(), pin["mult"].numpy(), pin["idx"].numpy(), t["max_gradient"])
+                assert engine.stat("upload_overlapped") == overlap
+                assert engine.stat("frac_mult_one") == np.mean(t["mult"] == 1.0)
+                assert same_bits(engine.jacobian(0, t["indep"], t["dep"]), want), (overlap, schedule)
+        # pageable memory and compaction take the sequential path
+        engine.set_option("overlap_upload", 1)
+        engine.upload_tape(t["stmt"], t["mult"], t["idx"], t["max_gradient"])
+        assert engine.stat("upload_overlapped") == 0
+        engine.set_option("remove_null", 1)
+        engine.upload_tape(pin["stmt"].numpy(), pin["mult"].numpy(), pin["idx"].numpy(), t["max_gradient"])
+        assert engine.stat("upload_overlapped") == 0
+        assert same_bits(engine.jacobian(0, t["indep"], t["dep"]), want)
+    finally:
+        engine.set_option("remove_null", 0)
+        engine.set_option("overlap_upload", 1)
+        engine.set_option("schedule", 0)
+        engine.set_option("smallg", 1)
