@@ -1227,10 +1227,12 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     // balanced kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
     // groups are kept for the streams below
     // 16 column blocks per CTA (two per warp) measured best on BASELINE config 4's shape: 8 and 16 within 1 %, 32 about 4 % slower
+    // ... and when a device holds few directions (one rank of eight: 16 column blocks), smaller CTAs on more streams:
+    // 1024 directions of config 4: 16 per CTA 949 ms, 8 on two streams 771 ms, 4 on four streams 701 ms
     int cbs = kFwdCbsDefault;
     if (c->opt_cbs > 0) cbs = int(std::min<int64_t>(c->opt_cbs, kFwdCbs));
     else if (F.n_colblocks < kFwdCbsDefault * c->opt_streams)
-      cbs = std::max(std::min(8, F.n_colblocks), (F.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
+      cbs = std::max(std::min(2, F.n_colblocks), (F.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
     cbs = std::max(1, std::min(cbs, kFwdCbs));
     F.cbs = cbs;
     const int bwarps = std::max(1, std::min(plan.warps, cbs));
@@ -1243,7 +1245,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     // wide steps: two direction halves on two streams still pay (the tail of one half's step is filled by the other's
     // next step: 3 % on config 4's shape); more streams only re-read the record stream
     if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= (balanced ? kWideStepCtas / 4 : kWideStepCtas))
-      nstr = std::min(nstr, balanced ? 2 : 1);
+      nstr = std::min(nstr, balanced ? (all_cb >= 4 * kFwdCbsDefault ? 2 : c->opt_streams) : 1);
     if (c->opt_wide_streams > 0) nstr = std::max(1, std::min<int>(c->opt_wide_streams, groups));
     if (c->opt_time_kernels || c->opt_profile_every) nstr = 1;
     s.stat["sweep_streams"] = nstr;
