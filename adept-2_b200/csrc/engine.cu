@@ -565,6 +565,7 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
   const size_t dense_smem = dense_tab + kWinStageBytes;   // table + cp.async staging of statements and operands
   const bool dense = dense_tab <= (size_t(160) << 10) && size_t(n_windows) * dense_tab <= (size_t(2) << 30);
   Buf& wstate = s.pool[33];
+  Buf& oplev = s.pool[46];   // hash variant: local step of every operation's statement, for the packing pass
   RET(ensure(errp, s.level, size_t(s.n_stmt) * 4));
   RET(ensure(errp, wdepth, size_t(n_windows + 1) * 4));
   RET(ensure(errp, wbase, size_t(n_windows + 1) * 4));
@@ -589,9 +590,10 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
     CK(cudaStreamSynchronize(s.stream));
     RET(ensure(errp, tables, size_t(std::max<int64_t>(total_entries, 1)) * sizeof(SlotEntry)));
     CK(cudaMemsetAsync(tables.p, 0xFF, size_t(total_entries) * sizeof(SlotEntry), s.stream));
+    RET(ensure(errp, oplev, size_t(std::max<int64_t>(O, 1)) * 4));
     window_levels_kernel<<<unsigned((n_windows * 32 + 127) / 128), 128, 0, s.stream>>>(
         s.stmt.as<int2>(), s.n_stmt, s.idx.as<int32_t>(), win_lo.as<int64_t>(), n_windows, tables.as<SlotEntry>(),
-        tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>());
+        tab_off.as<int64_t>(), s.level.as<int32_t>(), wdepth.as<int32_t>(), oplev.as<int32_t>());
     s.launches += 1;
   }
   lap("an_window_ms");
@@ -641,9 +643,10 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
         PA.gr = gr.as<int32_t>();
         PA.need = need.as<int32_t>();
         PA.gmap = gmap.as<int32_t>();
+        PA.oplev = dense ? nullptr : oplev.as<int32_t>();
         PA.dense = dense ? 1 : 0;
         void* args[] = {&PA};
-        const unsigned grid = unsigned(s.sm_count * std::min(per_sm, 2));
+        const unsigned grid = unsigned(s.sm_count * std::min(per_sm, 4));
         if (cudaLaunchCooperativeKernel((void*)window_pack_kernel, dim3(grid), dim3(256), args, 0, s.stream) == cudaSuccess) {
           packed = true;
           s.launches += 1;

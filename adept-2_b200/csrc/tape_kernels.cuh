@@ -234,7 +234,7 @@ __device__ __forceinline__ SlotEntry* table_entry(SlotEntry* T, uint32_t mask, i
 
 // One statement, the whole warp: lanes share its operands (any number of them) and its LHS.  Returns its local step.
 __device__ __forceinline__ int32_t window_walk_one(SlotEntry* T, uint32_t mask, const int32_t* __restrict__ idx, int64_t o0,
-                                                   int64_t o1, int32_t lhs, int lane) {
+                                                   int64_t o1, int32_t lhs, int lane, int32_t* __restrict__ oplev) {
   const int64_t nops = o1 - o0;
   int32_t lv = 1;
   if (nops < 32) {
@@ -274,6 +274,8 @@ __device__ __forceinline__ int32_t window_walk_one(SlotEntry* T, uint32_t mask, 
     if (lane == 0) __stcg(reinterpret_cast<int2*>(&eL->wl), make_int2(lv, 0));
   }
   __syncwarp();
+  if (oplev)
+    for (int64_t o = o0 + lane; o < o1; o += 32) oplev[o] = lv;
   return lv;
 }
 
@@ -337,7 +339,10 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
                                                             const int64_t* __restrict__ win_lo,
                                                             int64_t n_windows, SlotEntry* __restrict__ tables,
                                                             const int64_t* __restrict__ tab_off,
-                                                            int32_t* __restrict__ level, int32_t* __restrict__ win_depth) {
+                                                            int32_t* __restrict__ level, int32_t* __restrict__ win_depth,
+                                                            int32_t* __restrict__ oplev) {
+  // oplev[o] = local step of the statement that owns operation o: the packing pass reads it instead of searching
+  // the statement table for every operation (left unwritten for one-statement windows: their step is 1)
   const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_windows) return;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     if (ngrp == 0) {   // statement s has eight operands or more: the whole warp takes it
       const int32_t b0 = __shfl_sync(0xffffffffu, c.beg, 0), e0 = __shfl_sync(0xffffffffu, c.end, 0);
       const int32_t lhs0 = __shfl_sync(0xffffffffu, c.lhs, 0);
-      const int32_t lv = window_walk_one(T, mask, idx, b0, e0, lhs0, lane);
+      const int32_t lv = window_walk_one(T, mask, idx, b0, e0, lhs0, lane, oplev);
       if (lane == 0) level[s] = lv;
       depth = max(depth, lv);
       o0 = e0;
@@ -433,7 +438,10 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     if (cm) ncommit = min(ncommit, (__ffs(cm) - 1) >> 3);   // the first group that shares a slot with an earlier one (>= 1)
     const bool commit = g < ncommit;
     const int32_t my_nops = c.end - c.beg;
-    if (commit && x >= 0 && q < my_nops) __stcg(&e->rl, v);                 // readers of the live version
+    if (commit && x >= 0 && q < my_nops) {
+      __stcg(&e->rl, v);                                                     // readers of the live version
+      oplev[c.beg + q] = v;
+    }
     __syncwarp();
     if (commit && q == my_nops) {                                            // the write retires the old version and its readers
       __stcg(reinterpret_cast<int2*>(&e->wl), make_int2(v, 0));
@@ -724,6 +732,7 @@ struct PackArgs {
   int32_t* gr;
   int32_t* need;
   int32_t* gmap;
+  const int32_t* oplev;     // local step of every operation's statement (hash variant), or null: search the statement table
   int dense;
 };
 
@@ -746,10 +755,9 @@ __global__ void __launch_bounds__(256) window_pack_kernel(PackArgs A) {
       int32_t bound, l;
       if (t < n_ops) {
         const int64_t o = o0 + t;
-        const int64_t s = stmt_of_op_range(A.stmt, lo, hi, o);
         const int32_t x = A.idx[o];
         bound = max(__ldcg(&A.gw[x]) + 1, __ldcg(&A.gr[x]));   // written by other SMs in the previous window's phase C
-        l = A.level[s];
+        l = (lo == hi) ? 1 : (A.oplev ? A.oplev[o] : A.level[stmt_of_op_range(A.stmt, lo, hi, o)]);
       } else {
         const int64_t s = lo + (t - n_ops);
         const int32_t x = A.stmt[s].x;
