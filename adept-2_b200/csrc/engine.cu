@@ -1245,10 +1245,10 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const int groups = (all_cb + gwidth - 1) / gwidth;
     int nstr = std::max(1, std::min<int>(c->opt_streams, groups));
     // only narrow steps leave the machine idle between launches; wide ones would just re-read the tape per stream
-    // wide steps: two direction halves on two streams still pay (the tail of one half's step is filled by the other's
-    // next step: 3 % on config 4's shape); more streams only re-read the record stream
-    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= (balanced ? kWideStepCtas / 4 : kWideStepCtas))
-      nstr = std::min(nstr, balanced ? (all_cb >= 4 * kFwdCbsDefault ? 2 : c->opt_streams) : 1);
+    // wide steps: with the balanced kernel independent direction ranges on separate streams still pay (the tail of one
+    // range's step is filled by another's next step; config 4's shape, 4096 directions: 1 stream 2.79 s, 2: 2.69 s,
+    // 4: 2.63 s; the record stream is re-read once per range, < 1 % of the traffic); the old kernel keeps one stream
+    if (double(s.n_chunks) / std::max(1, s.n_levels) * groups >= kWideStepCtas && !balanced) nstr = 1;
     if (c->opt_wide_streams > 0) nstr = std::max(1, std::min<int>(c->opt_wide_streams, groups));
     if (c->opt_time_kernels || c->opt_profile_every) nstr = 1;
     s.stat["sweep_streams"] = nstr;

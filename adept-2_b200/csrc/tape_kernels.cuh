@@ -358,7 +358,6 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
   SlotEntry* T = tables + tab_off[w];
   const uint32_t mask = static_cast<uint32_t>(tab_off[w + 1] - tab_off[w]) - 1u;
   const int g = lane >> 3, q = lane & 7;
-  const uint32_t lower = (g == 0) ? 0u : ((1u << (g * 8)) - 1u);   // the lanes of the groups before mine
   int32_t depth = 0;
   int64_t s = lo;
   bool warm = false;
@@ -393,39 +392,21 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     }
     // 2. ... then the loads that refill the window two rounds ahead (statements s+8..s+11 and their operand slots)
     const WalkTier f = walk_load_tier(stmt, idx, s + 8, hi, __shfl_sync(0xffffffffu, n.end, 24), g, q);
-    // 3. the probe's answer.  Open addressing, and NO atomics: this warp is the only one that touches the window's
-    //    table, so a slot met for the first time (most are: a window touches ~3e5 distinct slots ~1.2 times each) is
-    //    entered with a plain store.  Lanes with the same slot land on the same entry; two DIFFERENT new slots that
-    //    found the same empty entry are told apart with a match.any over the entry numbers, the higher lane moves on.
-    //    Every new slot is entered whether or not its statement commits this round (so that a lane that moved on can
-    //    rely on the entry it skipped being taken).
+    // 3. the probe's answer (open addressing: walk on from h when the first entry belongs to another slot).
+    //    (A variant that enters new slots with plain stores and sorts out clashing entries with two more match.any
+    //    was measured 2x SLOWER than this CAS path -- 119 vs 58 ms on the 1e7-statement tape: match.any over 32
+    //    distinct values costs about as much as the DRAM round trip it was meant to save.)
     SlotEntry* e = nullptr;
     int32_t v = 1;
-    int32_t wl = -1, rl = -1;
-    bool fresh = false;
     if (x >= 0) {
-      int4 pr = probe;
-      for (;;) {
-        if (pr.x == x) { wl = pr.z; rl = pr.w; break; }
-        if (pr.x == -1) { fresh = true; break; }
-        h = (h + 1) & mask;
-        pr = __ldcg(reinterpret_cast<const int4*>(&T[h]));
+      int32_t wl, rl;
+      if (probe.x == x) {
+        e = &T[h];
+        wl = probe.z;
+        rl = probe.w;
+      } else {
+        e = table_entry(T, mask, x, wl, rl);
       }
-    }
-    const uint32_t same = __match_any_sync(0xffffffffu, x);
-    for (;;) {
-      const uint32_t hm = __match_any_sync(0xffffffffu, fresh ? h : (0x80000000u | static_cast<uint32_t>(lane)));
-      const bool clash = fresh && (hm & ~same & ((1u << lane) - 1u)) != 0u;
-      if (!__any_sync(0xffffffffu, clash)) break;
-      if (clash)
-        for (;;) {   // the slot is not in the table: the next empty entry is its place
-          h = (h + 1) & mask;
-          if (__ldcg(reinterpret_cast<const int4*>(&T[h])).x == -1) break;
-        }
-    }
-    if (x >= 0) {
-      e = &T[h];
-      if (fresh) __stcg(reinterpret_cast<int4*>(e), make_int4(x, 0, -1, -1));
       const int32_t nops = c.end - c.beg;
       v = (q < nops) ? max(wl + 1, rl) : max(wl, rl) + 1;   // RAW (strict), MONO (non-strict) | WAW, WAR (strict)
       v = max(v, 1);
@@ -433,7 +414,14 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
     v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
     v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));   // the statement's step, in all eight lanes of its group
-    const uint32_t cm = __ballot_sync(0xffffffffu, x >= 0 && (same & lower) != 0u);
+    // a slot shared with a statement of an EARLIER group of the round?  24 shuffles: cheaper than match.any
+    bool shared = false;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+      const int32_t ox = __shfl_sync(0xffffffffu, x, j);
+      if ((j >> 3) < g && ox == x) shared = true;
+    }
+    const uint32_t cm = __ballot_sync(0xffffffffu, x >= 0 && shared);
     int ncommit = ngrp;
     if (cm) ncommit = min(ncommit, (__ffs(cm) - 1) >> 3);   // the first group that shares a slot with an earlier one (>= 1)
     const bool commit = g < ncommit;
