@@ -86,7 +86,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region.  The nvidia-smi process is started BEFORE the
+    warm-up steps (its start-up takes driver locks for a few hundred ms, which would otherwise land inside a short timed
+    region) and only the samples that arrive between mark_begin() and stop() are used."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -96,31 +98,39 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.t_begin = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
+        t_end = time.perf_counter()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)          # one more sample for very short regions
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for (t, r) in self.rows if t0 <= t <= t_end + 0.15] or [r for (_, r) in self.rows[-3:]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -590,13 +600,14 @@ def main():
             eng.jacobian_device(mode, indep, dep, out_ptr)   # collective when world > 1
             return eng.stat("replay_ms", 0.0), eng.stat("sweep_ms", 0.0), eng.stat("sweep_launches", 0.0)
 
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and with_clocks:
+            sampler.start()
         for _ in range(n_warm):
             step()
         launches0 = eng.stat("kernel_launches", 0.0)
-        sampler = ClockSampler(local_rank)
         barrier()
-        if rank == 0 and with_clocks:
-            sampler.start()
+        sampler.mark_begin()
         t0 = time.perf_counter()
         ev_ms = sw_ms = sw_launches = 0.0
         for _ in range(n_steps):

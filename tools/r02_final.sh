@@ -23,7 +23,7 @@ for spec in "synthetic1e8_fwd 0 50" "synthetic1e8_fwd 1 50"; do
   cat gpurun_out/${T}_traffic_$tag.json
 done
 # one full capture of the dominant kernel (a wide step in the middle of the forward sweep of the 1e7 tape: same shape, 1/10 length)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:forward_balanced -s 1400 -c 2 -o gpurun_out/${T}_ncu_forward_balanced -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:forward_balanced -s 1254 -c 1 -o gpurun_out/${T}_ncu_forward_balanced -f \
    python bench.py --workload synthetic1e7_fwd --no-cpu-baseline --e2e-steps 0 --reverse-steps 0 --steps 1 --warmup 3 --opt wide_streams=1 > gpurun_out/${T}_ncu_full.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${T}_launches_synthetic1e7_fwd.csv \
    python bench.py --workload synthetic1e7_fwd --no-cpu-baseline --e2e-steps 0 --reverse-steps 0 --steps 1 --warmup 3 > gpurun_out/${T}_ncu_launches.log 2>&1
