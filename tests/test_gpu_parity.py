@@ -182,6 +182,38 @@ def test_levels_match_the_sequential_rule(engine, po, pkg, window):
         engine.set_option("coop_pack", 1)
 
 
+def chain_tape(n=20000, n_slots=40000):
+    """A serial chain y_k = a_k*y_{k-1} + b_k*x (every statement depends on the one before it) through fresh slots:
+    ONE window holds more local steps than the packing pass keeps in shared memory (4096), and with 40 000 slots the
+    walk uses the hash-table variant."""
+    rng = np.random.default_rng(11)
+    stmt = np.empty((n + 1, 2), np.int32)
+    stmt[0] = (-1, 0)
+    idx = np.empty(2 * n, np.int32)
+    idx[0::2] = np.r_[0, 1 + np.arange(n - 1)]       # y_{k-1} (x for the first)
+    idx[1::2] = 0                                     # x
+    stmt[1:, 0] = 1 + np.arange(n)
+    stmt[1:, 1] = 2 * (1 + np.arange(n))
+    return dict(stmt=stmt, mult=rng.uniform(0.9, 1.1, 2 * n), idx=idx, max_gradient=n_slots,
+                indep=np.array([0], np.int32), dep=np.array([n, n // 2, 7], np.int32))
+
+
+@pytest.mark.parametrize("coop", [1, 0])
+def test_a_window_deeper_than_the_shared_step_table(engine, po, coop):
+    t = chain_tape()
+    steps, want = po.levels(t["stmt"], t["idx"], t["max_gradient"], 2, window=65536, huge=65536, pack=1)
+    assert steps == 20000
+    try:
+        engine.set_option("coop_pack", coop)
+        upload(engine, t, LEVELS)
+        assert engine.stat("n_levels") == steps and np.array_equal(engine.levels(), want)
+        check_jacobians(engine, po, t, f"serial chain, coop_pack {coop}")
+        g0 = np.zeros(t["max_gradient"]); g0[t["dep"]] = [1.0, -2.0, 0.5]
+        assert same_bits(engine.adjoint(g0), po.adjoint(t["stmt"], t["mult"], t["idx"], g0))
+    finally:
+        engine.set_option("coop_pack", 1)
+
+
 # ---- adversarial little tapes: slot reuse, self reference, repeated operands, empty statements -----
 @pytest.mark.parametrize("seed", range(6))
 def test_random_tapes(engine, po, pkg, seed):
