@@ -1492,14 +1492,15 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
           continue;
         }
         const int64_t c0 = s.step_tchunk[l], c1 = s.step_tchunk[l + 1];
-        launch_pdl(reverse_snapshot_kernel<V, 4>, dim3(unsigned((n * ncols + 255) / 256)), dim3(256), st, pdl,
-                   s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
-                   s.aflag.as<uint8_t>(), B.flag_pitch, ncols, cb_lo);
+        if (launch_pdl(reverse_snapshot_kernel<V, 4>, dim3(unsigned((n * ncols + 255) / 256)), dim3(256), st, pdl,
+                       s.sched_lhs.as<int32_t>(), j0, n, g, s.abuf.as<double>(), K, n_dirs, s.rowact.as<uint8_t>(),
+                       s.aflag.as<uint8_t>(), B.flag_pitch, ncols, cb_lo) != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         nl[i] += 1;
         if (c1 > c0) {
           Bi.first_chunk = c0;
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-          launch_pdl(reverse_target_kernel<V>, dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), dim3(twarps * 32), st, pdl, Bi);
+          if (launch_pdl(reverse_target_kernel<V>, dim3(unsigned(c1 - c0), unsigned(g_hi - g_lo)), dim3(twarps * 32), st, pdl, Bi) !=
+              cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
           nl[i] += 1;
         }
