@@ -783,6 +783,21 @@ int build_schedule(const adept_cuda_ctx* c, Shard& s) {
       s.foff.as<int64_t>(), flag.as<int32_t>(), cid.as<int32_t>(), S, R, n_chunks, lfirst.as<int64_t>(), n_levels,
       s.fwd_chunk.as<int64_t>(), nullptr, lchunk.as<int64_t>());
   s.launches += 1;
+  {  // the balanced forward kernel stages a chunk in ONE piece: verify that every chunk of a step not flagged long fits
+    RET(ensure(errp, s.scratch, 64));
+    CK(cudaMemsetAsync(s.scratch.p, 0, 64, s.stream));
+    max_short_chunk_kernel<<<grid_for(n_levels, T, s.sm_count), T, 0, s.stream>>>(
+        lchunk.as<int64_t>(), s.fwd_chunk.as<int64_t>(), s.pool[45].as<uint8_t>(), n_levels,
+        reinterpret_cast<unsigned long long*>(s.scratch.p));
+    s.launches += 1;
+    unsigned long long longest = 0;
+    CK(cudaMemcpyAsync(&longest, s.scratch.p, 8, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    s.stat["max_short_chunk_recs"] = double(longest);
+    if (longest > (unsigned long long)kPieceRecs)
+      return fail(errp, ADEPT_CUDA_ERR_CUDA, "internal: a %llu-record chunk in a step not flagged long (staging holds %d)", longest,
+                  kPieceRecs);
+  }
   RET(ensure(errp, s.fwd_l, size_t(R) * sizeof(Rec)));
   if (!mult_settled) {   // the first reader of the multipliers: wait for an overlapped upload, screen them
     RET(settle_multipliers(c, s));
@@ -894,7 +909,8 @@ void publish_schedule_stats(adept_cuda_ctx* c) {
   c->stat["have_levels"] = s.have_levels ? 1.0 : 0.0;
   c->stat["kernel_launches"] = c->total_launches();
   for (const char* k : {"analysis_ms", "an_validate_ms", "an_window_ms", "an_pack_ms", "an_forward_ms", "an_target_ms", "an_fused_ms",
-                        "frac_mult_zero", "frac_mult_one", "frac_mult_minus_one", "ops_removed", "n_ops_recorded"}) {
+                        "frac_mult_zero", "frac_mult_one", "frac_mult_minus_one", "ops_removed", "n_ops_recorded",
+                        "max_short_chunk_recs"}) {
     auto it = s.stat.find(k);
     if (it != s.stat.end()) c->stat[k] = it->second;
   }

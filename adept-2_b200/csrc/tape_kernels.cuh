@@ -922,6 +922,25 @@ __global__ void mark_long_levels_kernel(const int64_t* __restrict__ foff, const 
     if (foff[j + 1] - foff[j] > thresh) flag[sched_level[j]] = 1;
 }
 
+// Guard of the balanced forward kernel's one-staged-piece assumption: out[0] = the longest chunk (in records) of any
+// step that is NOT flagged long.  The host refuses the schedule when that exceeds the staging buffer -- a wrong flag
+// must fail loudly at upload, not write past shared memory in a sweep.
+__global__ void max_short_chunk_kernel(const int64_t* __restrict__ level_chunk, const int64_t* __restrict__ fwd_chunk,
+                                       const uint8_t* __restrict__ level_long, int32_t n_levels,
+                                       unsigned long long* __restrict__ out) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  unsigned long long m = 0;
+  for (int64_t l = 1 + t; l <= n_levels; l += stride) {
+    if (level_long[l]) continue;
+    for (int64_t c = level_chunk[l]; c < level_chunk[l + 1]; ++c) {
+      const unsigned long long len = static_cast<unsigned long long>(fwd_chunk[c + 1] - fwd_chunk[c]);
+      m = len > m ? len : m;
+    }
+  }
+  if (m) atomicMax(out, m);
+}
+
 // chunk tables: fwd_chunk[c] = foff[j] for the c-th flagged j; fwd_chunk[n_chunks] = R;
 // rev_chunk[c'] = R - fwd_chunk[n_chunks - c']; level_chunk[l] = chunk id of level_first[l].
 __global__ void chunk_tables_kernel(const int64_t* __restrict__ foff, const int32_t* __restrict__ flag,

@@ -608,3 +608,34 @@ def test_overlapped_multiplier_upload_from_pinned_memory(engine, po, pkg):
         engine.set_option("overlap_upload", 1)
         engine.set_option("schedule", 0)
         engine.set_option("smallg", 1)
+
+
+@pytest.mark.parametrize("chunk", [0, 64, 128, 200, 256])
+def test_statements_around_the_staging_limit(engine, po, chunk):
+    """forward_balanced_kernel stages a chunk in ONE 256-record piece; steps that hold a statement long enough for a
+    chunk to exceed that go to forward_level_kernel (the host decides per step, and refuses the schedule if a chunk of
+    a step it did not flag is longer: stat max_short_chunk_recs).  Statements of 90..190 operands sit right on that
+    line for every chunk length."""
+    rng = np.random.default_rng(77 + chunk)
+    n_in, n_mid = 260, 420
+    stmt, mult, idx = [[-1, 0]], [], []
+    for k in range(n_mid):                       # layer 1: long statements over the inputs
+        ops = rng.choice(n_in, int(rng.integers(90, 191)), replace=False)
+        idx += list(ops); mult += list(rng.uniform(-0.2, 0.2, ops.size))
+        stmt.append([n_in + k, len(idx)])
+    for k in range(300):                         # layer 2: short and long statements mixed, over layer 1
+        ops = rng.choice(n_mid, int(rng.choice([3, 5, 120, 127, 128, 129, 160])), replace=False)
+        idx += list(n_in + ops); mult += list(rng.uniform(-0.2, 0.2, ops.size))
+        stmt.append([n_in + n_mid + k, len(idx)])
+    t = dict(stmt=np.array(stmt, np.int32), mult=np.array(mult), idx=np.array(idx, np.int32), max_gradient=n_in + n_mid + 300,
+             indep=np.arange(0, n_in, 3).astype(np.int32), dep=(n_in + n_mid + np.arange(0, 300, 7)).astype(np.int32))
+    try:
+        engine.set_option("chunk_recs", chunk)
+        for balanced in (1, 0):
+            engine.set_option("fwd_balanced", balanced)
+            upload(engine, t, LEVELS)
+            assert engine.stat("max_short_chunk_recs") <= 256
+            check_jacobians(engine, po, t, f"chunk {chunk} balanced {balanced}")
+    finally:
+        engine.set_option("chunk_recs", 0)
+        engine.set_option("fwd_balanced", 1)
