@@ -10,7 +10,9 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libadept_cuda.so")
+# $ADEPT_CUDA_LIB: another build of the same library, e.g. libadept_cuda_check.so (`make -C csrc CHECK=1`: device-side
+# bounds checks compiled in) to run the GPU test suite against
+LIB_PATH = os.environ.get("ADEPT_CUDA_LIB") or os.path.join(HERE, "libadept_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "adept_cuda.h")
 
 OK = 0

@@ -15,6 +15,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Device-side bounds checks of our own (this pool has no compute-sanitizer): `make CHECK=1` builds
+// ../libadept_cuda_check.so with -DADEPT_BOUNDS_CHECK, every ADEPT_DCHECK becomes a device assert (a failed one traps
+// the kernel and every later CUDA call fails loudly); $ADEPT_CUDA_LIB points the Python binding at that library, so
+// the whole GPU test suite can be run against it.  In the product build the macro expands to nothing.
+#ifdef ADEPT_BOUNDS_CHECK
+#include <assert.h>
+#define ADEPT_DCHECK(cond) assert(cond)
+#else
+#define ADEPT_DCHECK(cond) ((void)0)
+#endif
+
 namespace adept_b200 {
 
 struct __align__(16) Rec {

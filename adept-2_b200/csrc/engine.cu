@@ -1238,6 +1238,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     F.n_colblocks = int((n_dirs + 32 * V - 1) / (32 * V));
     F.flag_pitch = int(K / (32 * V));
     F.cb_lo = 0;
+    F.n_rows = s.max_gradient;
     int fwarps = std::max(1, std::min(plan.warps, F.n_colblocks));
     if (F.n_colblocks >= 16 && F.n_colblocks / fwarps < c->opt_streams)
       fwarps = std::max(1, std::min(fwarps, F.n_colblocks / std::max(1, c->opt_streams)));

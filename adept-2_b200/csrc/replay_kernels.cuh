@@ -944,6 +944,7 @@ struct ForwardArgs {
   int cb_lo;
   int flag_pitch;
   int cbs;           // forward_balanced_kernel: column blocks per CTA (<= kFwdCbs)
+  int64_t n_rows;    // rows of the workspace (bounds checks of the -DADEPT_BOUNDS_CHECK build)
 };
 
 template <int V, bool SPARSE>
@@ -1065,7 +1066,7 @@ template <int V, bool SPARSE>
 __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
                                              const uint32_t* __restrict__ tailm, uint4* __restrict__ wl,
                                              double* __restrict__ gcol, uint8_t* __restrict__ ract, int64_t K, int ncb,
-                                             int lane) {
+                                             int lane, int64_t n_rows) {
   // list entry: x = low word of the row's byte offset | 1 (statement end) | 2 (load the row) | 4 (statement end whose
   // row currently holds data), y = high word, (z, w) = multiplier bits (operation) or z = row (statement end)
   LaneVec<V> acc;
@@ -1094,6 +1095,7 @@ __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, c
       const uint64_t mb = static_cast<uint64_t>(__double_as_longlong(rc.m));
       e.z = is_tail ? static_cast<uint32_t>(rc.slot) : static_cast<uint32_t>(mb);
       e.w = static_cast<uint32_t>(mb >> 32);
+      ADEPT_DCHECK(__popc(work & lt_mask) < 32 && rc.slot >= 0 && rc.slot < n_rows);
       wl[__popc(work & lt_mask)] = e;
     }
     __syncwarp();
@@ -1164,6 +1166,7 @@ __global__ void __launch_bounds__(256, 4) forward_balanced_kernel(ForwardArgs A)
   const int n = static_cast<int>(r1 - r0);   // <= kPieceRecs: the host sends longer chunks to forward_level_kernel
   const int cb0 = A.cb_lo + blockIdx.y * A.cbs;
   const int cbs = min(A.cbs, A.n_colblocks - cb0);
+  ADEPT_DCHECK(n >= 1 && n <= kPieceRecs && cbs >= 1 && cbs <= kFwdCbs && (cb0 + cbs) * 64 <= A.K);
   if (threadIdx.x == 0) {
     const uint32_t bytes = static_cast<uint32_t>(n) * static_cast<uint32_t>(sizeof(Rec));
     mbar_expect_tx(&full, bytes);
@@ -1203,7 +1206,7 @@ __global__ void __launch_bounds__(256, 4) forward_balanced_kernel(ForwardArgs A)
     const int w = __ffs(mm) - 1;
     const int cb = cb0 + w;
     forward_task<V, SPARSE>(r, n, &pf[w * kPfPitch], tailm, &wlist[warp][0],
-                            A.g + (static_cast<int64_t>(cb) * 32 + lane) * V, A.rowact + cb, A.K, ncb, lane);
+                            A.g + (static_cast<int64_t>(cb) * 32 + lane) * V, A.rowact + cb, A.K, ncb, lane, A.n_rows);
   }
 }
 

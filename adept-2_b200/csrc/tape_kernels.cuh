@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(128) window_levels_kernel(const int2* __restri
     const bool commit = g < ncommit;
     const int32_t my_nops = c.end - c.beg;
     if (commit && x >= 0 && q < my_nops) {
+      ADEPT_DCHECK(c.beg + q < c.end && s + g <= hi);
       __stcg(&e->rl, v);                                                     // readers of the live version
       oplev[c.beg + q] = v;
     }
@@ -749,6 +750,7 @@ __global__ void __launch_bounds__(256) window_pack_kernel(PackArgs A) {
         bound = max(__ldcg(&A.gw[x]), __ldcg(&A.gr[x])) + 1;
         l = A.level[s];
       }
+      ADEPT_DCHECK(l >= 1 && l <= depth);
       if (bound > 1) {
         if (l <= ns) atomicMax(&sneed[l - 1], bound);
         else atomicMax(&need[l - 1], bound);
@@ -781,7 +783,10 @@ __global__ void __launch_bounds__(256) window_pack_kernel(PackArgs A) {
     }
     __syncthreads();
     if (depth > kNeedSmem) grid.sync();   // (never with the default window length) readers of gmap[l >= kNeedSmem] wait for every CTA
-    auto G = [&](int32_t l1) -> int32_t { return l1 <= kNeedSmem ? sneed[l1 - 1] : __ldcg(&gmap[l1 - 1]); };
+    auto G = [&](int32_t l1) -> int32_t {
+      ADEPT_DCHECK(l1 >= 1 && l1 <= depth);
+      return l1 <= kNeedSmem ? sneed[l1 - 1] : __ldcg(&gmap[l1 - 1]);
+    };
     // ---- C. fold the window's final per-slot state into the global summary ----
     if (lo == hi) {
       // a window of one (huge) statement has no table: its operands are readers at its step, then its LHS is written
