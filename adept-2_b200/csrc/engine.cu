@@ -1244,6 +1244,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       fwarps = std::max(1, std::min(fwarps, F.n_colblocks / std::max(1, c->opt_streams)));
     const bool sparse = !s.has_nonfinite;
     const bool balanced = c->opt_fwd_balanced != 0;
+    s.stat["used_fwd_balanced"] = balanced ? 1.0 : 0.0;
     // balanced kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
     // groups are kept for the streams below
     // 16 column blocks per CTA (two per warp) measured best on BASELINE config 4's shape: 8 and 16 within 1 %, 32 about 4 % slower

@@ -627,6 +627,8 @@ def main():
                  (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
         if used_fused:
             kname[(1, 2.0)] = "reverse_fused_kernel<2>"
+        if eng.stat("used_fwd_balanced", 0.0):
+            kname[(0, 2.0)] = "forward_balanced_kernel<2,sparse>"
         bpo = alg_bytes_per_opdir(S, O, mode)
         # algorithmic bytes of this rank's share of the step; the two-kernel reverse form splits them
         # between the snapshot kernel (per-statement part) and the gather (per-operation part): the events bracket both

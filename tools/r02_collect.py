@@ -24,7 +24,7 @@ if os.path.exists(os.path.join(G, "r02b_gather_ceiling.jsonl")):
 
 # traffic.json for bench.py
 tr = json.load(open(os.path.join(P, "traffic.json")))
-for key, tag, kern, note in (("synthetic1e8_fwd", "synthetic1e8_fwd_m0", "forward_level_kernel<2,sparse>",
+for key, tag, kern, note in (("synthetic1e8_fwd", "synthetic1e8_fwd_m0", "forward_balanced_kernel<2,sparse>",
                               "BASELINE config 4 full size, forward sweep (forward_balanced_kernel): every 50th launch, all 8192 directions, one stream under the profiler"),
                              ("synthetic1e8_rev", "synthetic1e8_fwd_m1", "reverse_fused_kernel<2>",
                               "BASELINE config 4 full size, fused reverse sweep: every 50th launch of both passes, 4096 directions per pass, one stream under the profiler")):

@@ -4,6 +4,9 @@ mkdir -p gpurun_out
 T=${1:-r02z}
 ( time timeout 2400 python -m pytest tests -m gpu -q ) > gpurun_out/${T}_pytest.log 2>&1
 tail -4 gpurun_out/${T}_pytest.log
+# the same suite against the build with our own device-side bounds checks (make -C adept-2_b200/csrc CHECK=1)
+( time ADEPT_CUDA_LIB=$PWD/adept-2_b200/libadept_cuda_check.so timeout 2400 python -m pytest tests -m gpu -q -x ) > gpurun_out/${T}_pytest_check.log 2>&1
+tail -2 gpurun_out/${T}_pytest_check.log
 timeout 1500 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_synthetic1e8_fwd.json 2> gpurun_out/${T}_bench_synthetic1e8_fwd.err
 timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${T}_bench_synthetic1e8_fwd_ref.json 2> gpurun_out/${T}_bench_synthetic1e8_fwd_ref.err
 timeout 600 python bench.py --workload toon4096 > gpurun_out/${T}_bench_toon4096.json 2> gpurun_out/${T}_bench_toon4096.err
