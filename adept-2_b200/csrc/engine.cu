@@ -194,6 +194,7 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_fwd_v4 = 0;         // balanced forward kernel with FOUR doubles per lane (1024-byte row segments per warp)
   int opt_overlap_upload = 1; // multipliers in page-locked memory are uploaded on their own stream while the level analysis runs
   int opt_coop_pack = 1;      // window packing as one cooperative kernel (0: three launches per window)
   int opt_batch_chunks = 4;   // ensemble entry point: chunks per device through the copy-in / sweep / copy-out pipeline
@@ -1205,7 +1206,7 @@ int mark_pass(Shard& s) {
 
 // One sweep over the resident pass (g already zeroed and seeded).  mode: 0 forward, 1 reverse.
 int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t K, int64_t n_dirs,
-                 const SweepPlan& plan, bool fused) {
+                 const SweepPlan& plan, bool fused, int V_fwd = 2) {
   std::string* errp = &s.err;
   if (s.R == 0) return 0;
   ReplayArgs A{};
@@ -1228,7 +1229,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     if (c->opt_time_kernels) RET(mark(s));
     s.launches += 1;
   } else if (mode == 0) {
-    constexpr int V = 2;
+    const int V = V_fwd;   // doubles per lane: 2, or 4 (forward_balanced_kernel<4>: 1024-byte row segments per warp)
     ForwardArgs F;
     F.recs = s.fwd_l.as<Rec>();
     F.chunk_begin = s.fwd_chunk.as<int64_t>();
@@ -1245,14 +1246,16 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
     const bool sparse = !s.has_nonfinite;
     const bool balanced = c->opt_fwd_balanced != 0;
     s.stat["used_fwd_balanced"] = balanced ? 1.0 : 0.0;
+    s.stat["fwd_lane_doubles"] = double(V);
     // balanced kernel: a CTA covers `cbs` column blocks and its warps take the active ones in turn; enough column
     // groups are kept for the streams below
     // 16 column blocks per CTA (two per warp) measured best on BASELINE config 4's shape: 8 and 16 within 1 %, 32 about 4 % slower
     // ... and when a device holds few directions (one rank of eight: 16 column blocks), smaller CTAs on more streams:
     // 1024 directions of config 4: 16 per CTA 949 ms, 8 on two streams 771 ms, 4 on four streams 701 ms
-    int cbs = kFwdCbsDefault;
+    const int cbs_default = V == 4 ? kFwdCbsDefault / 2 : kFwdCbsDefault;   // the same directions per CTA
+    int cbs = cbs_default;
     if (c->opt_cbs > 0) cbs = int(std::min<int64_t>(c->opt_cbs, kFwdCbs));
-    else if (F.n_colblocks < kFwdCbsDefault * c->opt_streams)
+    else if (F.n_colblocks < cbs_default * c->opt_streams)
       cbs = std::max(std::min(2, F.n_colblocks), (F.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
     cbs = std::max(1, std::min(cbs, kFwdCbs));
     F.cbs = cbs;
@@ -1308,12 +1311,15 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
             cudaProfilerStart();
         }
         cudaError_t le;
-        if (use_bal) {
-          if (sparse) le = launch_pdl(forward_balanced_kernel<V, true>, grid, block, st, pdl && !prof, Fi);
-          else le = launch_pdl(forward_balanced_kernel<V, false>, grid, block, st, pdl && !prof, Fi);
-        } else {
-          if (sparse) le = launch_pdl(forward_level_kernel<V, true>, grid, block, st, pdl && !prof, Fi);
-          else le = launch_pdl(forward_level_kernel<V, false>, grid, block, st, pdl && !prof, Fi);
+        if (use_bal && V == 4) {
+          if (sparse) le = launch_pdl(forward_balanced_kernel<4, true>, grid, block, st, pdl && !prof, Fi);
+          else le = launch_pdl(forward_balanced_kernel<4, false>, grid, block, st, pdl && !prof, Fi);
+        } else if (use_bal) {
+          if (sparse) le = launch_pdl(forward_balanced_kernel<2, true>, grid, block, st, pdl && !prof, Fi);
+          else le = launch_pdl(forward_balanced_kernel<2, false>, grid, block, st, pdl && !prof, Fi);
+        } else {   // (V == 2 here: shard_enqueue keeps four doubles per lane for tapes without long steps)
+          if (sparse) le = launch_pdl(forward_level_kernel<2, true>, grid, block, st, pdl && !prof, Fi);
+          else le = launch_pdl(forward_level_kernel<2, false>, grid, block, st, pdl && !prof, Fi);
         }
         if (le != cudaSuccess) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
         if (prof) {
@@ -1675,12 +1681,16 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       pass = std::min(pass, (((D + np - 1) / np + 63) / 64) * 64);
     }
     if (c->opt_pass_dirs > 0) pass = std::min<int64_t>(pass, ((c->opt_pass_dirs + 31) / 32) * 32);
-    const int64_t K = ((pass + 63) / 64) * 64;   // rows padded so that 16-byte lane vectors never leave a row
+    // doubles per lane in the level kernels: 2; 4 for the balanced forward kernel when asked for ("fwd_v4") and the tape
+    // has no step that must go to forward_level_kernel (the two kernels of one sweep must agree on the block width)
+    bool any_long = false;
+    for (uint8_t f : s.level_long) any_long |= (f != 0);
+    const int V = (mode == 0 && plan0.use_levels && c->opt_fwd_v4 && c->opt_fwd_balanced && !any_long) ? 4 : 2;
+    const int64_t K = ((pass + 32 * V - 1) / (32 * V)) * (32 * V);   // rows padded so that lane vectors never leave a row
     RET(ensure(errp, s.g, size_t(n_rows) * size_t(K) * 8));
     double* g = s.g.as<double>();
     int n_passes = 0;
     const SweepPlan plan = plan_sweep(c, s, std::min(D, pass));
-    const int V = 2;                               // doubles per lane in the level-reverse kernels
     const int ncb_pass = int(K / (32 * V));
     const bool sparse = plan.use_levels;
     const int32_t* out_rows_dev = out_slots_dev;
@@ -1706,7 +1716,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
       RET(mark_pass(s));
       {
         const double l0 = s.launches;
-        RET(launch_sweep(c, s, mode, g, K, n, plan, fused));
+        RET(launch_sweep(c, s, mode, g, K, n, plan, fused, V));
         s.sweep_launches += s.launches - l0;
       }
       RET(mark_pass(s));
@@ -2908,6 +2918,8 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_fused = value ? 1 : 0;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
+  } else if (k == "fwd_v4") {
+    c->opt_fwd_v4 = value ? 1 : 0;
   } else if (k == "overlap_upload") {
     c->opt_overlap_upload = value ? 1 : 0;
   } else if (k == "coop_pack") {

@@ -275,6 +275,21 @@ struct LaneVec<2> {
   __device__ __forceinline__ void zero() { x = 0.0; y = 0.0; }
 };
 
+template <>
+struct LaneVec<4> {   // four adjacent directions per lane: 1024 bytes per warp and row (forward_balanced_kernel<4>)
+  double x, y, z, w;
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0];
+    const double2 b = reinterpret_cast<const double2*>(p)[1];
+    x = a.x; y = a.y; z = b.x; w = b.y;
+  }
+  __device__ __forceinline__ void store(double* p) const {
+    reinterpret_cast<double2*>(p)[0] = make_double2(x, y);
+    reinterpret_cast<double2*>(p)[1] = make_double2(z, w);
+  }
+  __device__ __forceinline__ void zero() { x = 0.0; y = 0.0; z = 0.0; w = 0.0; }
+};
+
 // One thread looks at one (statement, column block) pair; the active pairs of the CTA are
 // compacted in shared memory and moved one row segment per warp.
 template <int V, int RB>
@@ -1100,12 +1115,13 @@ __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, c
     }
     __syncwarp();
     const int cnt = __popc(work);
-    for (int j = 0; j < cnt; j += kBatch) {
-      LaneVec<V> v[kBatch];
+    constexpr int NB = (V == 4) ? kBatch / 2 : kBatch;   // row loads in flight per lane: the same bytes for V = 2 and 4
+    for (int j = 0; j < cnt; j += NB) {
+      LaneVec<V> v[NB];
       // all loads of a step are independent of its stores (RAW/WAR between the statements of a step are excluded
       // by the schedule; a statement's own operands precede its end)
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < NB; ++u) {
         v[u].zero();
         if (j + u < cnt) {
           const uint2 e = *reinterpret_cast<const uint2*>(&wl[j + u]);
@@ -1114,7 +1130,7 @@ __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, c
         }
       }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < NB; ++u) {
         if (j + u >= cnt) break;
         const uint4 e = wl[j + u];
         if (e.x & 1u) {   // the statement is complete
@@ -1130,11 +1146,10 @@ __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, c
           open_active = false;
         } else {
           const double m = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(e.w) << 32) | e.z));
-          acc.x = mul_add_rn(acc.x, m, v[u].x);
-          if (V == 2) {
-            double* cv = reinterpret_cast<double*>(&acc);
-            cv[V - 1] = mul_add_rn(cv[V - 1], m, reinterpret_cast<const double*>(&v[u])[V - 1]);
-          }
+          double* cv = reinterpret_cast<double*>(&acc);
+          const double* av = reinterpret_cast<const double*>(&v[u]);
+#pragma unroll
+          for (int k = 0; k < V; ++k) cv[k] = mul_add_rn(cv[k], m, av[k]);
           open_active = true;
         }
       }
@@ -1143,8 +1158,9 @@ __device__ __forceinline__ void forward_task(const Rec* __restrict__ r, int n, c
   }
 }
 
+// (V = 4 needs ~80 registers: three CTAs per SM instead of four, each with twice the bytes in flight per lane)
 template <int V, bool SPARSE>
-__global__ void __launch_bounds__(256, 4) forward_balanced_kernel(ForwardArgs A) {
+__global__ void __launch_bounds__(256, (V == 4 ? 3 : 4)) forward_balanced_kernel(ForwardArgs A) {
   __shared__ __align__(16) Rec recs[kPieceRecs];
   __shared__ __align__(8) uint64_t full;
   __shared__ __align__(4) uint8_t pf[kFwdCbs * kPfPitch];   // pf[w*kPfPitch + i]: record i, column block cb0 + w
@@ -1166,7 +1182,7 @@ __global__ void __launch_bounds__(256, 4) forward_balanced_kernel(ForwardArgs A)
   const int n = static_cast<int>(r1 - r0);   // <= kPieceRecs: the host sends longer chunks to forward_level_kernel
   const int cb0 = A.cb_lo + blockIdx.y * A.cbs;
   const int cbs = min(A.cbs, A.n_colblocks - cb0);
-  ADEPT_DCHECK(n >= 1 && n <= kPieceRecs && cbs >= 1 && cbs <= kFwdCbs && (cb0 + cbs) * 64 <= A.K);
+  ADEPT_DCHECK(n >= 1 && n <= kPieceRecs && cbs >= 1 && cbs <= kFwdCbs && (cb0 + cbs) * 32 * V <= A.K);
   if (threadIdx.x == 0) {
     const uint32_t bytes = static_cast<uint32_t>(n) * static_cast<uint32_t>(sizeof(Rec));
     mbar_expect_tx(&full, bytes);

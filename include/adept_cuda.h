@@ -69,6 +69,9 @@ void adept_cuda_destroy(adept_cuda_ctx* ctx);
 int  adept_cuda_unique_id(void* id128);
 int  adept_cuda_join(adept_cuda_ctx* ctx, const void* id128, int rank, int world_size);
 int  adept_cuda_share_tape(adept_cuda_ctx* ctx, int root_rank);
+/* Collective calls (share_tape, jacobian*) agree on their status before any data-path collective: an error on one rank
+   (a root without a tape, a slot out of range, a malformed tape, a failed allocation) is returned by EVERY rank; no
+   rank is left waiting inside a broadcast or a gather. */
 
 /* ---- the tape ------------------------------------------------------------------------ */
 
@@ -80,7 +83,11 @@ int  adept_cuda_share_tape(adept_cuda_ctx* ctx, int root_rank);
    call (staged through pinned memory, cudaMemcpyAsync); pinned caller memory is DMA'd
    directly.  `epoch` is an opaque caller tag (e.g. a recording counter) returned by
    adept_cuda_tape_epoch so a shim can tell whether its host tape changed.
-   Also builds the device-side replay streams and the level schedule. */
+   Also validates the tape and builds the level schedule and the forward record stream on the device (the reverse streams
+   are built by the first reverse sweep).  Multipliers in page-locked memory (adept_cuda_host_alloc, cudaHostRegister)
+   are uploaded on a stream of their own WHILE the analysis runs -- it reads only statements and indices -- and are
+   complete on return like everything else.  In a one-process-per-GPU job (adept_cuda_join) the schedule is NOT built
+   here but by adept_cuda_share_tape, on all ranks at the same time (or by the first replay call). */
 int  adept_cuda_upload_tape(adept_cuda_ctx* ctx, const void* statements, int64_t n_stmt,
                             const double* multiplier, const int32_t* index, int64_t n_ops,
                             int64_t max_gradient, uint64_t epoch);
@@ -193,6 +200,8 @@ void  adept_cuda_host_free(void* p);
      "fwd_balanced"  1 (default) = the level-scheduled forward sweep uses forward_balanced_kernel (a CTA owns a chunk and
                      up to 32 column blocks, its warps take the active ones in turn and walk a compacted list) for every step
                      whose chunks fit one staged piece; 0 = forward_level_kernel (warp bound to a column block) throughout
+     "fwd_v4"        1 = the balanced forward kernel keeps FOUR adjacent directions per lane (1024-byte row segments per warp,
+                     128-direction column blocks) on tapes without over-long steps; 0 (default) = two
      "wide_streams"  N > 0: spread the forward level sweep over N streams even when its steps are wide (default 0: two
                      streams on wide steps, "streams" on narrow ones)
      "overlap_upload" 1 (default) = when the multiplier array is in page-locked memory it is uploaded on a stream of its own

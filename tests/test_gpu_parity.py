@@ -108,6 +108,44 @@ def test_forward_level_sweep_both_cta_shapes(engine, name, balanced, cbs, stream
         engine.set_option("pass_dirs", 0)
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_balanced_kernel_with_four_doubles_per_lane(engine, po, pkg, name):
+    """Option fwd_v4: the balanced forward kernel with 128-direction column blocks (32-byte lane vectors).  Tapes with an
+    over-long step keep two doubles per lane (both kernels of a sweep must agree on the block width)."""
+    g = load_golden(name)
+    try:
+        engine.set_option("fwd_v4", 1)
+        for window, cbs, pass_dirs in ((0, 0, 0), (80, 3, 0), (0, 0, 128), (80, 1, 64)):
+            upload(engine, g, LEVELS, window)
+            engine.set_option("cbs", cbs)
+            engine.set_option("pass_dirs", pass_dirs)
+            assert same_bits(engine.jacobian(0, g["indep"], g["dep"]), g["jac_fwd"]), (window, cbs, pass_dirs)
+            assert same_bits(engine.jacobian(1, g["indep"], g["dep"]), g["jac_rev"])     # reverse is unaffected
+        if name.startswith("toon") or name.startswith("synthetic"):
+            engine.set_option("cbs", 0)
+            engine.set_option("pass_dirs", 0)
+            engine.jacobian(0, g["indep"], g["dep"])
+            assert engine.stat("fwd_lane_doubles") == 4
+    finally:
+        engine.set_option("fwd_v4", 0)
+        engine.set_option("cbs", 0)
+        engine.set_option("pass_dirs", 0)
+
+
+def test_fwd_v4_on_config4_shape_and_non_finite(engine, po, pkg):
+    t = pkg.tapegen.synthetic_tape(120_000, 13, 200, seed=21)     # 200 directions: a ragged last 128-direction block
+    try:
+        engine.set_option("fwd_v4", 1)
+        upload(engine, t, LEVELS)
+        check_jacobians(engine, po, t, "fwd_v4 synthetic")
+        assert engine.stat("fwd_lane_doubles") == 4
+        t["mult"][::997] = np.inf                                   # non-sparse variant of the kernel
+        upload(engine, t, LEVELS)
+        check_jacobians(engine, po, t, "fwd_v4 synthetic, non-finite multipliers")
+    finally:
+        engine.set_option("fwd_v4", 0)
+
+
 def broadcast_tape(n=700, fan=64, seed=1):
     """x0, x1 feed EVERY statement of a layer (y_i = a_i x0 + b_i x1), and a second layer mixes the y's:
     in the reverse sweep x0 and x1 each receive n contributions within one step -- one target group of more
