@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "replay_kernels.cuh"
 #include "persistent_kernels.cuh"
+#include "fused_persistent_kernels.cuh"
 #include "smallg_kernels.cuh"
 #include "sweep1_kernels.cuh"
 #include "tape_kernels.cuh"
@@ -96,6 +97,10 @@ struct Shard {
   // fused reverse stream (versioned rows, one kernel per step; built on first need)
   bool have_fused = false;
   Buf ftgt, fchunk, fpar, out_rows, done, trace;
+  Buf d_step_fchunk, pcnt, pabort;    // resident fused kernel: device copy of step_fchunk, per-step counters, abort word
+  bool persist_checked = false;       // a resident fused kernel ran since the last shard_finish: look at pabort
+  int64_t max_step_fchunks = 0;       // widest step of the fused stream, in chunks
+  int64_t max_fchunk_recs = 0;        // longest chunk of the fused stream, in records (> kPieceRecs: streamed in pieces)
   int64_t n_fchunks = 0, R_f = 0, chunk_recs = 0;
   std::vector<int64_t> step_fchunk;   // [n_levels+2] first fused chunk of each step
   Buf d_level_first, d_step_tchunk, d_step_group;  // device copies of the step tables (persistent / small-G kernels)
@@ -194,6 +199,12 @@ struct adept_cuda_ctx {
   int opt_fused = 1;    // level-scheduled reverse sweep as ONE kernel per step over versioned rows (0: snapshot + gather)
   int opt_cbs = 0;      // fused kernel: column blocks per CTA (0 = automatic)
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
+  int opt_fused_persistent = 0;    // fused reverse sweep as ONE resident kernel with per-step participant counters
+                                   // (fused_persistent_kernels.cuh): 1 always, 0 never, -1 when the steps are narrow
+  int opt_auto_split = 0;          // 1: few directions on the device -> the fused reverse kernels share a chunk between two CTAs
+  int opt_split = 0;               // fused reverse kernels: CTAs per (chunk, column group) (0 = automatic, 1..16)
+  int opt_sub = 0;                 // ... and records per sub-task (0 = automatic, 4..256)
+  int64_t opt_spin_limit = int64_t(1) << 24;   // polls after which a waiting CTA of that kernel gives up (error, not a hang)
   int opt_fwd_v4 = 0;         // balanced forward kernel with FOUR doubles per lane (1024-byte row segments per warp)
   int opt_overlap_upload = 1; // multipliers in page-locked memory are uploaded on their own stream while the level analysis runs
   int opt_coop_pack = 1;      // window packing as one cooperative kernel (0: three launches per window)
@@ -1054,6 +1065,14 @@ int ensure_target_stream(const adept_cuda_ctx* c, Shard& s) {
   return 0;
 }
 
+__global__ void max_chunk_len_kernel(const int64_t* __restrict__ chunk_begin, int64_t n_chunks, unsigned long long* out) {
+  unsigned long long m = 0;
+  for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n_chunks; c += int64_t(gridDim.x) * blockDim.x)
+    m = max(m, static_cast<unsigned long long>(chunk_begin[c + 1] - chunk_begin[c]));
+  m = __reduce_max_sync(0xffffffffu, static_cast<unsigned int>(m));   // chunks are shorter than 2^31 records (R_f < 2^31)
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // Fused reverse stream over versioned rows (tape_kernels.cuh, "FUSED reverse stream"; the sequential statement of
 // the construction is tests/test_fused_stream_model.py).  Built on first need.
 int ensure_fused_stream(const adept_cuda_ctx* c, Shard& s) {
@@ -1123,7 +1142,20 @@ int ensure_fused_stream(const adept_cuda_ctx* c, Shard& s) {
   std::vector<int64_t> step_group_unused;
   RET(build_group_tables(s, n_groups, s.R_f, goff.as<int64_t>(), gstep.as<int32_t>(), s.fchunk, &s.n_fchunks, step_group_unused,
                          s.step_fchunk, nullptr));
+  RET(ensure(errp, s.scratch, 64));
+  CK(cudaMemsetAsync(s.scratch.p, 0, 8, s.stream));
+  max_chunk_len_kernel<<<grid_for(s.n_fchunks, T, s.sm_count), T, 0, s.stream>>>(s.fchunk.as<int64_t>(), s.n_fchunks,
+                                                                                 s.scratch.as<unsigned long long>());
+  unsigned long long longest_chunk = 0;
+  CK(cudaMemcpyAsync(&longest_chunk, s.scratch.p, 8, cudaMemcpyDeviceToHost, s.stream));
+  RET(ensure(errp, s.d_step_fchunk, size_t(n_levels + 2) * 8));
+  CK(cudaMemcpyAsync(s.d_step_fchunk.p, s.step_fchunk.data(), size_t(n_levels + 2) * 8, cudaMemcpyHostToDevice, s.stream));
+  s.max_step_fchunks = 0;
+  for (int32_t l = 1; l <= n_levels; ++l) s.max_step_fchunks = std::max(s.max_step_fchunks, s.step_fchunk[l + 1] - s.step_fchunk[l]);
+  CK(cudaStreamSynchronize(s.stream));
   CK(cudaGetLastError());
+  s.max_fchunk_recs = int64_t(longest_chunk);
+  s.stat["max_fused_chunk_recs"] = double(longest_chunk);
   s.stat["an_fused_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   s.stat["fused_records"] = double(s.R_f);
   s.have_fused = true;
@@ -1386,8 +1418,99 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
       cbs = std::max(std::min(8, B.n_colblocks), (B.n_colblocks + c->opt_streams - 1) / std::max(1, c->opt_streams));
     cbs = std::max(1, std::min(cbs, kFusedCbs));
     B.cbs = cbs;
+    // Work distribution of the fused kernels.  A Jacobian's activity is banded: of a step's chunks only those whose
+    // targets lie within reach of this device's directions have anything to do, and there all column blocks at once.
+    // When the device holds few directions (one rank of several) a step is a few busy CTAs, each warp walking a whole
+    // chunk (BASELINE config 2 at 512 directions: 18 us of dependent row loads per step on a mostly idle machine).
+    // Then every chunk goes to `split` CTAs and is cut into sub-tasks of `sub` records (replay_kernels.cuh).
+    {
+      int split = 1, sub = 0;
+      const double ctas = double(s.n_fchunks) / std::max(1, s.n_levels) * ((B.n_colblocks + cbs - 1) / cbs);
+      const double resident = 4.0 * s.sm_count;
+      // measured on config 2 (sweep of one Jacobian, ms; profiles/r02s_*): 512 directions 41.3 / 32.7 / 37.0 / 51.4 for
+      // split 1 / 2 / 4 / 8, 1024 directions 41.2 / 37.1 / 48.9 / 80.6, 2048 directions 48.5 / 60.6 / 92.8: every extra
+      // CTA costs its launch, staging and activity round trip, so two per chunk, and only with few directions
+      if (c->opt_auto_split && fused && B.n_colblocks <= 16 && ctas > 0 && ctas < resident && s.max_fchunk_recs <= kPieceRecs) split = 2;
+      if (c->opt_split > 0) split = c->opt_split;
+      if (split > 1) sub = int(std::max<int64_t>(8, (s.chunk_recs > 0 ? s.chunk_recs : kChunkRecs) / split));
+      if (c->opt_sub > 0) sub = c->opt_sub;
+      B.split = fused ? split : 1;
+      B.sub = fused ? sub : 0;
+      s.stat["fused_split"] = double(B.split);
+      s.stat["fused_sub"] = double(B.sub);
+    }
     if (fused) twarps = std::max(1, std::min(plan.warps, cbs));
     const int gwidth = fused ? cbs : twarps;   // column blocks per CTA row
+    if (fused && c->opt_fused_persistent != 0 && !c->opt_time_kernels && !c->opt_profile_every && s.n_fchunks > 0) {
+      // ONE resident kernel for the whole pass (fused_persistent_kernels.cuh) when the steps are narrow: items of a
+      // step = chunks x column groups; a step that does not fill the resident grid twice is all launch, drain and refill
+      int pcbs = c->opt_cbs > 0 ? int(std::min<int64_t>(c->opt_cbs, kFusedCbs)) : std::min(kFusedCbs, B.n_colblocks);
+      pcbs = std::max(1, pcbs);
+      const int pgy = (B.n_colblocks + pcbs - 1) / pcbs;
+      const int pwarps = std::max(1, std::min(plan.warps, pcbs));
+      int per_sm = 0;
+      cudaError_t oe;
+      if (B.ref_block == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reverse_fused_persistent_kernel<V, 0>, pwarps * 32, 0);
+      else if (B.ref_block == 2) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reverse_fused_persistent_kernel<V, 1>, pwarps * 32, 0);
+      else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reverse_fused_persistent_kernel<V, 2>, pwarps * 32, 0);
+      CK(oe);
+      const int64_t resident = int64_t(per_sm) * s.sm_count;
+      const double items_avg = double(s.n_fchunks) / std::max(1, s.n_levels) * pgy;
+      const bool narrow = items_avg < 2.0 * double(resident);
+      if (resident >= 1 && (c->opt_fused_persistent > 0 || narrow)) {
+        FusedPersistArgs PA{};
+        PA.T = B;
+        PA.T.cbs = pcbs;
+        PA.T.cb_lo = 0;
+        PA.T.n_tail = 0;
+        PA.T.done = nullptr;
+        PA.step_fchunk = s.d_step_fchunk.as<int64_t>();
+        PA.n_levels = s.n_levels;
+        PA.gy = pgy;
+        RET(ensure(errp, s.pcnt, size_t(s.n_levels + 2) * sizeof(unsigned int)));
+        if (!s.pabort.p) {
+          RET(ensure(errp, s.pabort, 128));
+          CK(cudaMemsetAsync(s.pabort.p, 0, 128, s.stream));
+        }
+        CK(cudaMemsetAsync(s.pcnt.p, 0, size_t(s.n_levels + 2) * sizeof(unsigned int), s.stream));
+        PA.cnt = s.pcnt.as<unsigned int>();
+        PA.abort = s.pabort.as<unsigned int>();
+        PA.spin_limit = static_cast<unsigned int>(c->opt_spin_limit);
+        const int64_t G = std::max<int64_t>(1, std::min(resident, s.max_step_fchunks * pgy * PA.T.split));
+#ifdef ADEPT_FUSED_TRACE
+        const char* ptrace_file = getenv("ADEPT_CUDA_TRACE_FILE");
+        if (ptrace_file && *ptrace_file) {
+          RET(ensure(errp, s.trace, size_t(8192) * 4 * 8));
+          CK(cudaMemsetAsync(s.trace.p, 0, size_t(8192) * 4 * 8, s.stream));
+          PA.trace = s.trace.as<unsigned long long>();
+        }
+#endif
+        void* args[] = {&PA};
+        const void* fn = B.ref_block == 1   ? (const void*)reverse_fused_persistent_kernel<V, 0>
+                         : B.ref_block == 2 ? (const void*)reverse_fused_persistent_kernel<V, 1>
+                                            : (const void*)reverse_fused_persistent_kernel<V, 2>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(unsigned(G)), dim3(unsigned(pwarps * 32)), args, 0, s.stream));
+        s.launches += 1;
+        s.persist_checked = true;
+        s.stat["sweep_streams"] = 1;
+        s.stat["used_fused_persistent"] = 1.0;
+        s.stat["persistent_grid"] = double(G);
+        s.stat["persistent_cbs"] = double(pcbs);
+        CK(cudaGetLastError());
+#ifdef ADEPT_FUSED_TRACE
+        if (PA.trace) {   // profiling aid: the clock stamps of CTA 0's items (wait begins, wait ends, activity bytes in, item done)
+          CK(cudaStreamSynchronize(s.stream));
+          std::vector<unsigned long long> h(size_t(8192) * 4);
+          CK(cudaMemcpy(h.data(), s.trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+          if (FILE* f = fopen(ptrace_file, "w")) {
+            for (size_t q = 0; q < 8192 && h[q * 4 + 3]; ++q) fprintf(f, "%llu %llu %llu %llu\n", h[q * 4], h[q * 4 + 1], h[q * 4 + 2], h[q * 4 + 3]);
+            fclose(f);
+          }
+        }
+#endif
+        return 0;
+      }
+    }
     if (!fused && c->opt_persistent && s.n_tchunks > 0) {
       // one cooperative kernel walks all steps (persistent_kernels.cuh)
       PersistArgs PA;
@@ -1489,7 +1612,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
           Bi.trace = (i == 0 && trace_on && nl[0] < kTraceLaunches) ? s.trace.as<unsigned long long>() + size_t(nl[0]) * 8 : nullptr;
 #endif
           if (c->opt_time_kernels && mark(s)) { rcs[i] = ADEPT_CUDA_ERR_CUDA; return; }
-          const dim3 fgrid(unsigned(c1 - c0), unsigned(g_hi - g_lo)), fblock(twarps * 32);
+          const dim3 fgrid(unsigned((c1 - c0) * Bi.split), unsigned(g_hi - g_lo)), fblock(twarps * 32);
           const bool prof = c->opt_profile_every > 0 && (int64_t(nl[i]) % c->opt_profile_every) == 0;
           if (prof) {
             cudaStreamSynchronize(st);
@@ -1584,6 +1707,7 @@ int shard_enqueue(const adept_cuda_ctx* c, Shard& s, int mode, const int32_t* se
   s.sweep_launches = 0;
   CK(cudaEventRecord(s.ev[0], s.stream));
   s.stat["n_passes"] = 0;
+  s.stat["used_fused_persistent"] = 0.0;
   // tapes whose gradient list fits shared memory: one CTA per 32/64 directions walks all steps by itself
   if (D > 0 && c->opt_smallg && s.have_levels && c->opt_schedule != 1 && s.max_step_width < (int64_t(1) << 20)) {
     const size_t kSmemCap = size_t(220) << 10;
@@ -1742,6 +1866,15 @@ int shard_finish(Shard& s) {
   std::string* errp = &s.err;
   CK(cudaSetDevice(s.dev));
   CK(cudaStreamSynchronize(s.stream));
+  if (s.persist_checked) {   // the resident fused kernel: did a CTA give up waiting?
+    s.persist_checked = false;
+    unsigned int aborted = 0;
+    CK(cudaMemcpy(&aborted, s.pabort.p, sizeof aborted, cudaMemcpyDeviceToHost));
+    if (aborted) {
+      CK(cudaMemset(s.pabort.p, 0, 128));
+      return fail(errp, ADEPT_CUDA_ERR_CUDA, "resident fused reverse kernel: a CTA waited longer than spin_limit polls for the step above");
+    }
+  }
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
   s.stat["replay_ms"] = ms;                       // zero-fill + seed + sweep + extraction, all passes
@@ -2380,6 +2513,30 @@ int adept_cuda_create(adept_cuda_ctx** out, const int* devices, int n_devices) {
     }
     for (int k = 0; k < n_devices; ++k) c->sh[k].comm = comms[k];
   }
+  // $ADEPT_CUDA_OPTIONS = "key=value,key=value": option defaults for callers that only see the Stack API (the drop-in)
+  if (const char* env = getenv("ADEPT_CUDA_OPTIONS")) {
+    std::string all(env);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string kv = all.substr(pos, end - pos);
+      pos = end + 1;
+      const size_t eq = kv.find('=');
+      if (kv.empty()) continue;
+      int rc = ADEPT_CUDA_ERR_ARG;
+      if (eq != std::string::npos && eq > 0 && eq + 1 < kv.size()) {
+        char* endp = nullptr;
+        const long long v = strtoll(kv.c_str() + eq + 1, &endp, 10);
+        if (endp && *endp == 0) rc = adept_cuda_set_option(c, kv.substr(0, eq).c_str(), int64_t(v));
+      }
+      if (rc) {
+        fprintf(stderr, "adept_cuda_create: bad entry '%s' in $ADEPT_CUDA_OPTIONS: %s\n", kv.c_str(), c->err.c_str());
+        adept_cuda_destroy(c);
+        return rc;
+      }
+    }
+  }
   *out = c;
   return 0;
 }
@@ -2916,6 +3073,19 @@ int adept_cuda_set_option(adept_cuda_ctx* c, const char* key, int64_t value) {
     c->opt_smallg = value ? 1 : 0;
   } else if (k == "fused") {
     c->opt_fused = value ? 1 : 0;
+  } else if (k == "fused_persistent") {
+    c->opt_fused_persistent = value > 0 ? 1 : (value < 0 ? -1 : 0);
+  } else if (k == "auto_split") {
+    c->opt_auto_split = value ? 1 : 0;
+  } else if (k == "split") {
+    if (value < 0 || value > 16) return fail(errp, ADEPT_CUDA_ERR_ARG, "split must be in 0..16");
+    c->opt_split = int(value);
+  } else if (k == "sub") {
+    if (value != 0 && (value < 4 || value > 256)) return fail(errp, ADEPT_CUDA_ERR_ARG, "sub must be 0 or in 4..256");
+    c->opt_sub = int(value);
+  } else if (k == "spin_limit") {
+    if (value < 64 || value > (int64_t(1) << 31) - 1) return fail(errp, ADEPT_CUDA_ERR_ARG, "spin_limit must be in 64 .. 2^31-1");
+    c->opt_spin_limit = value;
   } else if (k == "tail") {
     c->opt_tail = value ? 1 : 0;
   } else if (k == "fwd_v4") {

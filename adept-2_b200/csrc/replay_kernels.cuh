@@ -375,6 +375,8 @@ struct TargetArgs {
   int64_t n_dirs;
   int ref_block;
   int cbs;           // reverse_fused_kernel: column blocks per CTA (<= kFusedCbs)
+  int split;         // fused kernels: CTAs per (chunk, column group), each owning a range of the chunk's sub-tasks (<= 1: one)
+  int sub;           // fused kernels: records per sub-task (<= 0: the whole piece is one)
   // reverse_fused_kernel: "tail" steps.  Steps of a chunk or two (boundary statements between two wide levels, scalar
   // chains) are not worth a launch of their own: the launch of the step before them carries them along, and the
   // CTA that finishes last (ticket counter *done) runs them one after the other.
@@ -679,9 +681,11 @@ __device__ __forceinline__ FusedLane fused_lane(const TargetArgs& A, int cb, int
 // LP: how the reference's P-lane skip rule (adept/jacobian.cpp:392-407) maps to lanes holding V = 2 directions:
 //   0  P = 1: per component;  1  P = 2: the lane's own pair;  2  P >= 4: P/2 adjacent lanes (warp ballot).
 template <int V, int LP>
-__device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, const uint8_t* __restrict__ pfw,
+__device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int i0, int i1, const uint8_t* __restrict__ pfw,
                                            const uint32_t* __restrict__ headm, uint4* __restrict__ wl,
                                            const FusedLane& L) {
+  // records [i0, i1) of the staged piece: i0 is a head (or i0 == i1), i1 is a head or the end of the piece, so the
+  // range holds whole target groups and ranges of one chunk can be walked by different warps (fused_subtask_range)
   // Per block of 32 records the lanes decode ONE record each (row byte offset = row * bytes per row, flags) and
   // park the heads and the active operations, compacted and in order, in the warp's list wl[]:
   //   x = low word of the byte offset | 1 (head) | 2 (row is active: load it), y = high word,
@@ -695,13 +699,13 @@ __device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, con
   uint32_t cur_row = 0u;
   bool dirty = false;
   const uint32_t lt_mask = (1u << L.lane) - 1u;
-  const int nblk = (n + 31) >> 5;
-  for (int blk = 0; blk < nblk; ++blk) {
+  const int nblk = (i1 + 31) >> 5;
+  for (int blk = i0 >> 5; blk < nblk; ++blk) {
     const int i = (blk << 5) + L.lane;
-    const bool valid = i < n;
+    const bool valid = i >= i0 && i < i1;
     const bool a = valid && pfw[i] != 0;
     const uint32_t act = __ballot_sync(0xffffffffu, a);
-    const uint32_t hm = headm[blk];
+    const uint32_t hm = headm[blk] & __ballot_sync(0xffffffffu, valid);
     const uint32_t work = act | hm;
     if (work == 0u) continue;
     if ((work >> L.lane) & 1u) {
@@ -777,7 +781,92 @@ __device__ __forceinline__ void fused_task(const Rec* __restrict__ r, int n, con
   }
 }
 
+// Sub-tasks of a staged piece: the piece is cut at the first head at or after every multiple of `sub` records.  A
+// Jacobian's activity is banded (a chunk's targets either see all of a device's directions or none), so with few
+// directions per device a step's work sits in a few CTAs whose warps each walk a whole chunk while most of the machine
+// idles.  The host then (TargetArgs::split, ::sub) gives every chunk to `split` CTAs, each owning a range of the
+// sub-tasks, and the warps of a CTA take (sub-task, active column block) pairs in turn: one or two batches of row
+// loads per warp instead of eight.  With many directions the machine is full anyway and sub = kPieceRecs, split = 1
+// keep the walks long (full batches).
+__device__ __forceinline__ int fused_first_head(const uint32_t* __restrict__ headm, int pos, int n) {
+  for (int blk = pos >> 5; (blk << 5) < n; ++blk) {
+    uint32_t w = headm[blk];
+    if (blk == (pos >> 5)) w &= 0xffffffffu << (pos & 31);
+    if (w) {
+      const int i = (blk << 5) + __ffs(w) - 1;
+      return i < n ? i : n;
+    }
+  }
+  return n;
+}
+// sub-task s of a piece of n records: [first head >= s*sub, first head >= (s+1)*sub)
+__device__ __forceinline__ void fused_subtask_range(const uint32_t* __restrict__ headm, int n, int sub, int s, int& i0, int& i1) {
+  i0 = (s == 0) ? 0 : fused_first_head(headm, s * sub, n);
+  i1 = ((s + 1) * sub >= n) ? n : fused_first_head(headm, (s + 1) * sub, n);
+}
+
 constexpr int kPfPitch = kPieceRecs + 4;   // bytes per column block of the activity table (+4: conflict-free columns)
+
+// The common case of both fused reverse kernels: a chunk that is ONE staged piece r[0, n).  The CTA owns the column
+// blocks [cb0, cb0 + cbs) and part `part` of `nparts` of the piece's sub-tasks.  All threads of the CTA call this;
+// between() runs after the activity bytes are in (a hook for the resident kernel's look-ahead).
+template <int V, int LP, class Between>
+__device__ __forceinline__ void fused_single_piece(const TargetArgs& A, const Rec* __restrict__ r, int n, int cb0, int cbs,
+                                                   int part, int nparts, uint8_t* pf, uint32_t* headm, uint4 (*wlist)[32],
+                                                   uint32_t* smask, Between between) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int ncb = A.flag_pitch;
+  // head mask of every block of 32 records
+  for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
+    const int32_t kind = i < n ? r[i].kind : REC_OP;
+    const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
+    if (lane == 0) headm[i >> 5] = h;
+  }
+  const int sub = A.sub > 0 ? A.sub : kPieceRecs;
+  const int nsub = (n + sub - 1) / sub;
+  int s_lo = 0, s_hi = nsub, i0 = 0, i1 = n;
+  if (nparts > 1) {   // my share of the sub-tasks and the records they cover
+    __syncthreads();
+    s_lo = part * nsub / nparts;
+    s_hi = (part + 1) * nsub / nparts;
+    i0 = (s_lo == 0) ? 0 : fused_first_head(headm, s_lo * sub, n);
+    i1 = (s_hi * sub >= n) ? n : fused_first_head(headm, s_hi * sub, n);
+    if (s_hi <= s_lo) i1 = i0;
+  }
+  ADEPT_DCHECK(0 <= i0 && i0 <= n && i1 <= n);
+  // activity bytes: thread t -> record i0 + t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
+  uint32_t seen = 0u;   // column blocks for which this thread saw an active contribution
+  for (int t = threadIdx.x; t < (i1 - i0) * cbs; t += blockDim.x) {
+    const int i = i0 + t / cbs, w = t % cbs;
+    const int32_t row = r[i].slot;
+    const int32_t kind = r[i].kind;
+    uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
+    uint8_t f = 0;
+    if (kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
+    else f = *b;
+    pf[w * kPfPitch + i] = f;
+    if (kind == REC_OP && f) seen |= 1u << w;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
+  if (lane == 0 && seen) atomicOr(smask, seen);
+  __syncthreads();
+  between();
+  const uint32_t mask = *smask;
+  // tasks = (sub-task) x (active column block), handed to the warps in turn from the last warp down (warp 0 hosts the
+  // thread that issues copies and looks ahead)
+  const int nact = __popc(mask);
+  for (int t = nwarps - 1 - warp; t < nact * (s_hi - s_lo); t += nwarps) {
+    const int sb = s_lo + t / nact;
+    const int w = __fns(mask, 0, t % nact + 1);
+    int j0, j1;
+    fused_subtask_range(headm, n, sub, sb, j0, j1);
+    if (j0 >= j1) continue;
+    const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
+    fused_task<V, LP>(r, j0, j1, &pf[w * kPfPitch], headm, &wlist[warp][0], L);
+  }
+}
 
 template <int V, int LP>
 __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
@@ -792,7 +881,9 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
   const int ncb = A.flag_pitch;
   // work items of this CTA: its own (chunk, column group) and, if it turns out to be the last CTA of a launch
   // that carries tail steps, every (chunk, column group) of those steps, step after step
-  int64_t c = A.first_chunk + blockIdx.x;
+  const int split = A.split > 1 ? A.split : 1;   // CTAs per (chunk, column group): each owns a range of the chunk's sub-tasks
+  int64_t c = A.first_chunk + blockIdx.x / split;
+  int part = static_cast<int>(blockIdx.x % split), nparts = split;
   int cby = blockIdx.y;
   int tail = -1;   // -1: own item; >= 0: tail step being run
   FUSED_TRACE_MIN(0);
@@ -820,38 +911,10 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       if (tail < 0) { FUSED_TRACE_MIN(1); FUSED_TRACE_MAX(2); }
       mbar_wait(&ring.full[0], 0u);
       const Rec* r = &ring.buf[0][0];
-      // head mask of every block of 32 records
-      for (int i = threadIdx.x; i < ((n + 31) & ~31); i += blockDim.x) {
-        const int32_t kind = i < n ? r[i].kind : REC_OP;
-        const uint32_t h = __ballot_sync(0xffffffffu, kind != REC_OP);
-        if (lane == 0) headm[i >> 5] = h;
-      }
-      // activity bytes: thread t -> record t / cbs, column block cb0 + t % cbs (consecutive bytes of a row)
-      uint32_t seen = 0u;   // column blocks for which this thread saw an active contribution
-      for (int t = threadIdx.x; t < n * cbs; t += blockDim.x) {
-        const int i = t / cbs, w = t - i * cbs;
-        const int32_t row = r[i].slot;
-        const int32_t kind = r[i].kind;
-        uint8_t* b = A.rowact + static_cast<int64_t>(row) * ncb + cb0 + w;
-        uint8_t f = 0;
-        if (kind == REC_ZMARK) *b = 0;   // new version of an LHS slot: +0.0 until a contribution lands
-        else f = *b;
-        pf[w * kPfPitch + i] = f;
-        if (kind == REC_OP && f) seen |= 1u << w;
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, d);
-      if (lane == 0 && seen) atomicOr(&smask, seen);
-      __syncthreads();
-      if (tail < 0) FUSED_TRACE_MAX(3);
-      const uint32_t mask = smask;
-      int k = 0;
-      for (uint32_t mm = mask; mm; mm &= mm - 1u, ++k) {
-        if (k % nwarps != warp) continue;
-        const int w = __ffs(mm) - 1;
-        const FusedLane L = fused_lane<V>(A, cb0 + w, lane);
-        fused_task<V, LP>(r, n, &pf[w * kPfPitch], headm, &wlist[warp][0], L);
-      }
+      fused_single_piece<V, LP>(A, r, n, cb0, cbs, part, nparts, pf, headm, wlist, &smask,
+                                [&]() { if (tail < 0) FUSED_TRACE_MAX(3); });
+    } else if (part != 0) {
+      if (tail < 0) pdl_wait();   // a long chunk is not split: it belongs to the first of its CTAs (the others may still run tails)
     } else {
       // ---- a chunk longer than one piece (a target group of more than kPieceRecs contributions): the chunk is
       // streamed once per set of nwarps column blocks, warp w bound to one column block, state carried across pieces
@@ -925,6 +988,8 @@ __global__ void __launch_bounds__(256, 4) reverse_fused_kernel(TargetArgs A) {
       tail = 0;
       c = A.tail_c0[0];
       cby = 0;
+      part = 0;     // a tail item is one chunk x one column group, whole
+      nparts = 1;
     } else {
       if (++cby == static_cast<int>(gridDim.y)) {
         cby = 0;

@@ -627,6 +627,9 @@ def main():
                  (0, 1.0): "replay_forward_kernel", (1, 3.0): "smallg_kernel<reverse>", (0, 3.0): "smallg_kernel<forward>"}
         if used_fused:
             kname[(1, 2.0)] = "reverse_fused_kernel<2>"
+        used_resident = used_fused and bool(eng.stat("used_fused_persistent", 0.0))
+        if used_resident:
+            kname[(1, 2.0)] = "reverse_fused_persistent_kernel<2>"
         if eng.stat("used_fwd_balanced", 0.0):
             kname[(0, 2.0)] = "forward_balanced_kernel<2,sparse>"
         bpo = alg_bytes_per_opdir(S, O, mode)
@@ -661,7 +664,9 @@ def main():
             except Exception:
                 pass
         engine_info = {"schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
-                       "fused_reverse": used_fused, "steps_in_schedule": eng.stat("n_levels", 0),
+                       "fused_reverse": used_fused, "resident_kernel": used_resident,
+                       "resident_grid": eng.stat("persistent_grid", None) if used_resident else None,
+                       "steps_in_schedule": eng.stat("n_levels", 0),
                        "pass_dirs": eng.stat("pass_dirs", 0), "n_passes": n_passes,
                        "host_issue_ms": eng.stat("host_issue_ms", None),
                        "l2": "inputs larger than L2: record stream %.0f MB + workspace %.0f MB per pass" %

@@ -193,6 +193,23 @@ void  adept_cuda_host_free(void* p);
                      32 reverse, 16 forward, fewer when a device holds few directions)
      "tail"          fused kernel: 1 (default) = steps of a chunk or two are run by the last CTA of the previous step's
                      launch instead of a launch of their own
+     "split"         fused reverse kernels, work distribution: every (chunk, column group) goes to `split` CTAs (1..16), each
+                     owning a range of the chunk's sub-tasks, whose warps take (sub-task, active column block) pairs in turn.
+                     0 (default) = automatic: one CTA walks the whole chunk, or see "auto_split".  Stat "fused_split"
+     "sub"           ... records per sub-task (4..256; sub-tasks are cut at target-group heads).  0 (default) = automatic: the
+                     chunk length divided by "split", at least 8.  Stat "fused_sub"
+     "auto_split"    1 = when the device holds few directions (<= 1024, e.g. one rank of eight), the steps are narrow and no
+                     chunk is longer than a staged piece, a chunk is shared by TWO CTAs: a Jacobian's activity is banded, so a
+                     step's work then sits in a few CTAs on a mostly idle machine (BASELINE config 2, 512 directions: 41 ->
+                     33 ms per Jacobian).  Default 0
+   Option defaults can also be given in the environment, for callers that only see the Stack API:
+     ADEPT_CUDA_OPTIONS="key=value,key=value" is applied by adept_cuda_create (a bad entry makes it fail).
+     "fused_persistent" the fused reverse sweep as ONE resident kernel for the whole pass: CTAs take the (chunk, column
+                     group) items of every step round robin, count themselves in per step and wait only for the participants
+                     of the step above; no launch, drain and refill per step.  1 = always, 0 = never, -1 (default) = when
+                     the steps are narrow (a step's items would not fill the resident grid twice).  Stat "used_fused_persistent"
+     "spin_limit"    polls (64 .. 2^31-1, default 2^24) after which a waiting CTA of that kernel gives up: the call then
+                     returns ADEPT_CUDA_ERR_CUDA instead of hanging the device
      "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
                      between steps (implies the two-kernel data layout); 0 (default): per-step launches, measured faster
      "time_kernels"  1 = bracket every launch of the dominant replay kernel with CUDA events
