@@ -201,7 +201,7 @@ struct adept_cuda_ctx {
   int opt_tail = 1;     // fused kernel: steps of a chunk or two ride along with the previous step's launch
   int opt_fused_persistent = 0;    // fused reverse sweep as ONE resident kernel with per-step participant counters
                                    // (fused_persistent_kernels.cuh): 1 always, 0 never, -1 when the steps are narrow
-  int opt_auto_split = 0;          // 1: few directions on the device -> the fused reverse kernels share a chunk between two CTAs
+  int opt_auto_split = 1;          // 1: few directions on the device -> the fused reverse kernels share a chunk between two CTAs
   int opt_split = 0;               // fused reverse kernels: CTAs per (chunk, column group) (0 = automatic, 1..16)
   int opt_sub = 0;                 // ... and records per sub-task (0 = automatic, 4..256)
   int64_t opt_spin_limit = int64_t(1) << 24;   // polls after which a waiting CTA of that kernel gives up (error, not a hang)

@@ -666,6 +666,8 @@ def main():
         engine_info = {"schedule": {1.0: "tape-ordered", 2.0: "level", 3.0: "level, shared-memory gradients"}.get(used, "?"),
                        "fused_reverse": used_fused, "resident_kernel": used_resident,
                        "resident_grid": eng.stat("persistent_grid", None) if used_resident else None,
+                       "fused_split": eng.stat("fused_split", None) if used_fused else None,
+                       "fused_sub": eng.stat("fused_sub", None) if used_fused else None,
                        "steps_in_schedule": eng.stat("n_levels", 0),
                        "pass_dirs": eng.stat("pass_dirs", 0), "n_passes": n_passes,
                        "host_issue_ms": eng.stat("host_issue_ms", None),

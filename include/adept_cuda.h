@@ -198,10 +198,10 @@ void  adept_cuda_host_free(void* p);
                      0 (default) = automatic: one CTA walks the whole chunk, or see "auto_split".  Stat "fused_split"
      "sub"           ... records per sub-task (4..256; sub-tasks are cut at target-group heads).  0 (default) = automatic: the
                      chunk length divided by "split", at least 8.  Stat "fused_sub"
-     "auto_split"    1 = when the device holds few directions (<= 1024, e.g. one rank of eight), the steps are narrow and no
+     "auto_split"    1 (default) = when the device holds few directions (<= 1024, e.g. one rank of eight), the steps are narrow and no
                      chunk is longer than a staged piece, a chunk is shared by TWO CTAs: a Jacobian's activity is banded, so a
                      step's work then sits in a few CTAs on a mostly idle machine (BASELINE config 2, 512 directions: 41 ->
-                     33 ms per Jacobian).  Default 0
+                     33 ms per Jacobian); 0 = never
    Option defaults can also be given in the environment, for callers that only see the Stack API:
      ADEPT_CUDA_OPTIONS="key=value,key=value" is applied by adept_cuda_create (a bad entry makes it fail).
      "fused_persistent" the fused reverse sweep as ONE resident kernel for the whole pass: CTAs take the (chunk, column

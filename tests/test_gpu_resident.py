@@ -142,11 +142,13 @@ def test_long_chunks_are_not_split(engine, po, persistent):
 
 
 def test_automatic_split_with_few_directions(engine, po, pkg):
-    """Few directions on the device (what one rank of eight holds): the engine splits the chunks by itself."""
+    """Option auto_split: few directions on the device (what one rank of eight holds) and narrow steps -> two CTAs per
+    chunk, chosen by the engine; not when a chunk is longer than a staged piece."""
     t = pkg.tapegen.advection_tape("toon", 1200, 8)
     sub = dict(t)
     sub["dep"] = t["dep"][100:228].copy()                   # 128 directions = 2 column blocks
     try:
+        engine.set_option("auto_split", 1)
         for persistent in (0, 1):
             engine.set_option("fused_persistent", persistent)
             engine.set_option("smallg", 0)
@@ -154,6 +156,37 @@ def test_automatic_split_with_few_directions(engine, po, pkg):
             got = engine.jacobian(1, sub["indep"], sub["dep"])
             rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], sub["indep"], sub["dep"], 1, n_threads=0)
             assert rc == 0 and same_bits(got, want)
-            assert engine.stat("fused_split") > 1 and engine.stat("fused_sub") >= 8
+            assert engine.stat("fused_split") == 2 and engine.stat("fused_sub") == 32
+        engine.set_option("fused_persistent", 0)
+        b = broadcast_tape()
+        upload(engine, b, LEVELS)
+        check_jacobians(engine, po, b, "broadcast, auto_split")
+        assert engine.stat("max_fused_chunk_recs") > 256 and engine.stat("fused_split") == 1
     finally:
         engine.set_option("fused_persistent", 0)
+        engine.set_option("auto_split", 0)
+
+
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_every_chunk_longer_than_a_piece_and_split(engine, po, pkg, persistent):
+    """chunk_recs = 256: nearly every chunk spills a few records into a second piece, so with split > 1 most items of
+    the resident kernel (and most CTAs of the per-step kernel) pass their chunk by -- also the FIRST item of a CTA (the
+    resident kernel once fetched a piece for it that nobody waited for; CPU model tests/test_persistent_ring_model.py)."""
+    t = pkg.tapegen.advection_tape("toon", 700, 5)
+    sub = dict(t)
+    sub["dep"] = t["dep"][::5].copy()
+    try:
+        engine.set_option("fused_persistent", persistent)
+        engine.set_option("smallg", 0)
+        engine.set_option("chunk_recs", 256)
+        upload(engine, t, LEVELS)
+        for split, cbs in ((8, 1), (3, 0), (1, 0)):
+            engine.set_option("split", split)
+            engine.set_option("cbs", cbs)
+            got = engine.jacobian(1, sub["indep"], sub["dep"])
+            rc, want = po.jacobian(t["stmt"], t["mult"], t["idx"], t["max_gradient"], sub["indep"], sub["dep"], 1, n_threads=0)
+            assert rc == 0 and same_bits(got, want), (split, cbs)
+        assert engine.stat("max_fused_chunk_recs") > 256
+    finally:
+        for k in ("fused_persistent", "split", "cbs", "chunk_recs"):
+            engine.set_option(k, 0)

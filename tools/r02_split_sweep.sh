@@ -1,6 +1,9 @@
+# Config 2 (Toon nx=4096 nt=1000, reverse) with few directions per device: chunks shared by 1/2/4/8 CTAs ("split"), one launch per
+# step and the resident kernel ("fused_persistent"), plus in-kernel time stamps from the trace build (make -C adept-2_b200/csrc TRACE=1).
+# Produced profiles/r02_split_*.json and profiles/r02_fused_trace_summary.txt.  NOTE: bound the pytest line (it once ran into a hang).
 mkdir -p gpurun_out
 T=r02s
-( time timeout 900 python -m pytest tests/test_gpu_resident.py tests/test_gpu_parity.py -m gpu -q -x -k "resident or golden_jacobians or tiny_steps or longer_than or overwritten or non_finite" ) > gpurun_out/${T}_pytest.log 2>&1
+( time timeout 120 python -m pytest tests/test_gpu_resident.py tests/test_gpu_parity.py -m gpu -q -x -k "resident or golden_jacobians or tiny_steps or longer_than or overwritten or non_finite" ) > gpurun_out/${T}_pytest.log 2>&1
 tail -6 gpurun_out/${T}_pytest.log
 B="--workload toon4096 --no-cpu-baseline --e2e-steps 0 --steps 8 --warmup 3"
 run() { name=$1; shift
