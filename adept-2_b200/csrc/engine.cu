@@ -1489,7 +1489,10 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         const void* fn = B.ref_block == 1   ? (const void*)reverse_fused_persistent_kernel<V, 0>
                          : B.ref_block == 2 ? (const void*)reverse_fused_persistent_kernel<V, 1>
                                             : (const void*)reverse_fused_persistent_kernel<V, 2>;
-        CK(cudaLaunchCooperativeKernel(fn, dim3(unsigned(G)), dim3(unsigned(pwarps * 32)), args, 0, s.stream));
+        if (cudaLaunchCooperativeKernel(fn, dim3(unsigned(G)), dim3(unsigned(pwarps * 32)), args, 0, s.stream) != cudaSuccess) {
+          cudaGetLastError();   // no cooperative launch on this device / in this context: one launch per step, below
+          goto per_step;
+        }
         s.launches += 1;
         s.persist_checked = true;
         s.stat["sweep_streams"] = 1;
@@ -1511,6 +1514,7 @@ int launch_sweep(const adept_cuda_ctx* c, Shard& s, int mode, double* g, int64_t
         return 0;
       }
     }
+  per_step:
     if (!fused && c->opt_persistent && s.n_tchunks > 0) {
       // one cooperative kernel walks all steps (persistent_kernels.cuh)
       PersistArgs PA;
