@@ -6,22 +6,31 @@
 // reverse_fused_kernel), item by item with the same device functions, so the arithmetic and every accumulation order are
 // those of the per-step kernel -- and of the reference (adept/jacobian.cpp:382-431).  What changes is who waits for whom:
 //
-//   * An ITEM is (chunk, column group) of a step.  The G resident CTAs (cooperative launch: co-residency is guaranteed)
-//     take the items of a step round robin (from a start that moves on after every step that fills the grid), so every CTA can enumerate its
-//     own items of the whole sweep without any communication (PCursor).
+//   * An ITEM is (chunk, column group, part) of a step -- part: which of the chunk's T.split ranges of sub-tasks
+//     (replay_kernels.cuh, fused_single_piece).  The G resident CTAs (cooperative launch: co-residency is guaranteed) take
+//     the items of a step round robin, from a start that moves on after every step that fills the grid, so every CTA can
+//     enumerate its own items of the whole sweep without any communication (PCursor).
 //   * There is no grid-wide barrier.  Step l has parts(l) = min(G, items(l)) participating CTAs, which every CTA can
 //     compute; a CTA counts itself in at cnt[l] after its last item of step l, and before its first item of step l it
 //     waits until the step processed before l (the next higher non-empty one) has all its participants counted in.  By
 //     induction that step's participants had waited for the one before, and so on: everything above l is complete.
 //     CTAs without items in a step neither arrive nor wait, and a CTA that was the only participant of the previous
 //     step goes on without touching global memory at all (the scalar chains between two wide steps).
-//   * The records are immutable, so the TMA copy of a CTA's NEXT item is issued before the current item is processed
-//     -- also across a step boundary, i.e. before the wait.
+//   * The records are immutable, so the TMA copy of a CTA's NEXT item is issued while the current item is processed
+//     (once its activity bytes are in) -- also across a step boundary, i.e. before the wait.
+//   CPU models: tests/test_persistent_cursor_model.py (items, counters, waits under random interleavings) and
+//   tests/test_persistent_ring_model.py (ring slots and mbarrier phases).
 //
-// Memory model: a CTA's stores of a step are ordered before its arrival by bar.sync + __threadfence() (release, gpu
-// scope); a waiter polls the counter with relaxed loads, then __threadfence() (acquire) + bar.sync order the loads of
-// all its threads after what the counter stands for.  A CTA that polls longer than spin_limit raises *abort and every
-// CTA leaves at its next wait: the host reports an error instead of hanging the device.
+// Memory model: a CTA's stores of a step are ordered before its arrival by bar.sync + fence.acq_rel.gpu (release); a
+// waiter polls the counter with relaxed loads, then fence.acq_rel.gpu (acquire) + bar.sync order the loads of all its
+// threads after what the counter stands for (the pattern of a cooperative-groups grid sync, per step and per
+// participant instead of per grid).  A CTA that polls longer than spin_limit raises *abort and every CTA leaves at its
+// next wait: the host reports an error instead of hanging the device.
+//
+// Measured (B200, BASELINE config 2; DESIGN.md section 5, "Narrow steps"): bit-identical, and SLOWER than one launch per
+// step on four PDL-chained streams (512 directions: 48 vs 41 ms; 4096: 126-145 vs 83 ms) -- an item costs ~2.5 us even
+// when its chunk lies outside the band of active targets.  Opt-in ("fused_persistent"); kept as the synchronisation
+// skeleton of a step that first lists the active (sub-task, column block) pairs device-wide and then hands them out.
 #pragma once
 #include "replay_kernels.cuh"
 
