@@ -206,8 +206,9 @@ void  adept_cuda_host_free(void* p);
      ADEPT_CUDA_OPTIONS="key=value,key=value" is applied by adept_cuda_create (a bad entry makes it fail).
      "fused_persistent" the fused reverse sweep as ONE resident kernel for the whole pass: CTAs take the (chunk, column
                      group) items of every step round robin, count themselves in per step and wait only for the participants
-                     of the step above; no launch, drain and refill per step.  1 = always, 0 = never, -1 (default) = when
-                     the steps are narrow (a step's items would not fill the resident grid twice).  Stat "used_fused_persistent"
+                     of the step above; no launch, drain and refill per step.  1 = always, -1 = when the steps are narrow (a
+                     step's items would not fill the resident grid twice), 0 (default) = never: bit-identical, but measured
+                     slower than one launch per step on this hardware.  Stat "used_fused_persistent"
      "spin_limit"    polls (64 .. 2^31-1, default 2^24) after which a waiting CTA of that kernel gives up: the call then
                      returns ADEPT_CUDA_ERR_CUDA instead of hanging the device
      "persistent"    1 = the level-scheduled reverse sweep runs as ONE cooperative kernel with grid-wide barriers
